@@ -1,0 +1,108 @@
+/* quanonet_b200 — C-ABI of the B200-native HEA statevector simulator.
+ *
+ * This is the drop-in boundary for the ONE hot path of Wang-Ruocheng/QuanONet: the batched
+ * statevector evaluation (+ adjoint gradients) of the hardware-efficient-ansatz circuit that the
+ * reference runs through TorchQuantum in core/quantum_circuits_tq.py (_TQHEACircuit.forward :65-104,
+ * ._measure :106-127; backward = loss.backward() at solvers/solver_pt.py:235).  The reference is pure
+ * Python and has no FFI of its own; these entry points are what a binding for that path would call
+ * (see INTEGRATION.md for the ctypes stub and the torch custom op built on it).
+ *
+ * Circuit in canonical form (host code canonicalises the reference's block_configs into it):
+ *   K blocks; block k = RX(x[b, k*n + q]) on every qubit q, then depth_per_block[k] >= 1 sublayers;
+ *   sublayer s = RY(w[s,2,q]) RZ(w[s,1,q]) RY(w[s,0,q]) on every qubit q (RY(w[s,0,q]) first), then the
+ *   CNOT ring control=(i+1)%n -> target=i, i = 0..n-1 (no ring when n == 1);  S = sum_k depth[k].
+ *   out[b] = <psi_b| H |psi_b>.   Qubit q is bit q of the amplitude index (qubit 0 = LSB).
+ *
+ * Ownership: the caller allocates every buffer (inputs, outputs, workspace); the library never
+ *   allocates, frees or keeps device pointers past return.
+ * Errors: 0 = success; negative = invalid argument (checked on the host before any launch);
+ *   positive = cudaError_t of a failed launch.  Never throws, never exits.  qon_last_error() returns
+ *   a thread-local message for the last non-zero return on this thread.
+ * Threading / streams: stateless and re-entrant.  All work is enqueued on `stream` (a cudaStream_t
+ *   passed as void*; NULL = legacy default stream) of the CURRENT device; no host synchronisation,
+ *   CUDA-graph capturable.  Two calls may share a workspace only if stream-ordered.
+ * Layout: x/gx rows are contiguous (row stride given in elements); w is (S,3,n) contiguous;
+ *   out/grad_out are (B,) contiguous.  Device pointers must be aligned to the element size.
+ */
+#ifndef QUANONET_B200_H
+#define QUANONET_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QON_ABI_VERSION 1
+
+/* dtype: arithmetic type of x, w, out, gradients and the state */
+#define QON_F32 0 /* float32 / complex64  — parity with the TorchQuantum path            */
+#define QON_F64 1 /* float64 / complex128 — parity with MindQuantum's double-precision path */
+
+/* observable */
+#define QON_HAM_DIAG 0    /* ham_diag given: H = diag(ham_diag); else H = offset + coeff * sum_q Z_q
+                             (core/quantum_circuits_tq.py:112-126, _ham_params :141-146)             */
+#define QON_HAM_PAULI_X 1 /* H = offset + coeff * sum_q X_q  (core/quantum_circuits_ms.py:28-39)     */
+#define QON_HAM_PAULI_Y 2 /* H = offset + coeff * sum_q Y_q                                          */
+
+/* index order of ham_diag */
+#define QON_DIAG_LSB0 0 /* entry k: qubit q = bit q of k — MindQuantum/Qiskit builders
+                           (core/quantum_circuits_ms.py:56-60)                                     */
+#define QON_DIAG_MSB0 1 /* entry k: wire 0 = most-significant bit — TorchQuantum get_states_1d order,
+                           what core/quantum_circuits_tq.py:112-114 multiplies against              */
+
+/* error codes (negative) */
+#define QON_ERR_BAD_ARG (-1)
+#define QON_ERR_UNSUPPORTED (-2)
+#define QON_ERR_WORKSPACE (-3)
+#define QON_ERR_NO_DEVICE (-4)
+
+int qon_abi_version(void);
+const char* qon_last_error(void);
+
+/* Bytes of device workspace needed by qon_hea_forward (need_grad = 0) or
+ * qon_hea_forward_backward (need_grad = 1) for this problem on the current device.
+ * Returns 0 and sets qon_last_error() on invalid arguments. */
+size_t qon_workspace_bytes(int64_t B, int n, int K, const int* depth_per_block, int dtype, int need_grad);
+
+/* Forward: out[b] = <psi_b|H|psi_b>.  Replaces _TQHEACircuit.forward + _measure
+ * (core/quantum_circuits_tq.py:65-127).
+ *   x               device, (B, n*K), row stride ldx elements
+ *   w               device, (S, 3, n)
+ *   out             device, (B,)
+ *   depth_per_block HOST, (K,) ints, each >= 1
+ *   ham_diag        device, (2^n,) or NULL
+ */
+int qon_hea_forward(const void* x, int64_t ldx, const void* w, void* out,
+                    int64_t B, int n, int K, const int* depth_per_block,
+                    const void* ham_diag, int diag_order, double ham_offset, double ham_coeff, int ham_kind,
+                    int dtype, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Forward + adjoint backward in one pass.  Replaces forward + autograd backward of the same module
+ * (what compare_backends.py:188-199 and solvers/solver_pt.py:233-235 exercise).
+ *   grad_out  device, (B,)          dL/dout
+ *   out       device, (B,)          written
+ *   grad_x    device, (B, n*K) row stride ldgx, or NULL to skip it (fixed-scale encoders)
+ *   grad_w    device, (S, 3, n)     OVERWRITTEN with sum_b grad_out[b] * dout[b]/dw
+ * The batch reduction of grad_w is deterministic (fixed summation order for a given B and device).
+ */
+int qon_hea_forward_backward(const void* x, int64_t ldx, const void* w, const void* grad_out,
+                             void* out, void* grad_x, int64_t ldgx, void* grad_w,
+                             int64_t B, int n, int K, const int* depth_per_block,
+                             const void* ham_diag, int diag_order, double ham_offset, double ham_coeff,
+                             int ham_kind, int dtype, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Which kernel tier a problem maps to on the current device: 0 = register tier (state in registers,
+ * 2^lanes_log2 lanes per sample), 1 = shared-memory tier, 2 = HBM-streamed tier; -1 = unsupported. */
+int qon_plan_tier(int64_t B, int n, int dtype, int need_grad, int* lanes_log2);
+
+/* FP32 FFMA-saturating micro-benchmark (the metric is "% of FP32 peak" and MEASURED_PEAKS.json has
+ * no FP32 entry): runs `iters` dependent-chain FFMA rounds on every SM and returns achieved
+ * TFLOP/s measured with CUDA events on `stream`; negative on error.  Synchronises the stream. */
+double qon_measure_fp32_peak_tflops(int iters, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QUANONET_B200_H */

@@ -1,0 +1,34 @@
+// Internal launch interface between the C-ABI translation unit (qon_capi.cu) and the kernel
+// instantiation units (hea_reg_f32.cu, hea_reg_f64.cu, hea_generic.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include "hea_common.cuh"
+
+namespace qon {
+
+struct RegLaunchInfo {
+    int threads;         // CTA size
+    int blocks_per_sm;   // resident CTAs per SM (occupancy API)
+    int regs;            // registers per thread
+    bool ok;             // the (NL, LQ) combination is instantiated
+};
+
+// mode: 0 = forward only, 1 = forward+backward with dL/dx, 2 = forward+backward without dL/dx
+RegLaunchInfo reg_info_f32(int nl, int lq, int mode);
+RegLaunchInfo reg_info_f64(int nl, int lq, int mode);
+cudaError_t reg_launch_f32(int nl, int lq, int mode, int grid, const HeaParams<float>& p, cudaStream_t st);
+cudaError_t reg_launch_f64(int nl, int lq, int mode, int grid, const HeaParams<double>& p, cudaStream_t st);
+
+struct GenericPlan {
+    int threads;
+    size_t smem_bytes;       // dynamic shared memory (0 when the state lives in HBM)
+    bool state_global;
+    int blocks_per_sm;
+};
+GenericPlan generic_plan(int n, int dtype, int mode);
+cudaError_t generic_launch_f32(int n, int mode, int grid, const GenericPlan& gp, const HeaParams<float>& p, int vp,
+                               float* gstate, cudaStream_t st);
+cudaError_t generic_launch_f64(int n, int mode, int grid, const GenericPlan& gp, const HeaParams<double>& p, int vp,
+                               double* gstate, cudaStream_t st);
+
+}  // namespace qon

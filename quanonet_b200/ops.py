@@ -1,0 +1,164 @@
+"""torch custom ops over the C-ABI: ``quanonet::hea_expval`` and ``quanonet::hea_expval_backward``.
+
+PyTorch is plumbing here — device memory, the current stream, autograd wiring.  The arithmetic is
+the hand-written CUDA in csrc/, reached through ``_lib`` (ctypes).  CUDA tensors only; a CPU tensor
+raises (no fallback).
+
+Inputs are in the C-ABI's canonical form (see include/quanonet_b200.h): ``x (B, n*K)``,
+``weights (S,3,n)``, ``depth_per_block`` (K ints >= 1).  The reference-facing module
+(core/quantum_circuits_tq.py) canonicalises arbitrary ``block_configs`` before calling in.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Tuple
+
+import torch
+
+from . import _lib
+
+_DTYPES = {torch.float32: _lib.QON_F32, torch.float64: _lib.QON_F64}
+
+
+def _check_inputs(x, weights, n_wires, depth_per_block, ham_diag):
+    if not x.is_cuda:
+        raise RuntimeError("quanonet::hea_expval runs on CUDA tensors only (there is no CPU fallback); "
+                           f"got x on {x.device}")
+    if x.dtype not in _DTYPES:
+        raise TypeError(f"x must be float32 or float64, got {x.dtype}")
+    if weights.dtype != x.dtype or weights.device != x.device:
+        raise TypeError("weights must match x in dtype and device")
+    K = len(depth_per_block)
+    S = int(sum(depth_per_block))
+    if x.dim() != 2 or x.shape[1] != n_wires * K:
+        raise ValueError(f"x must be (B, n*K) = (B, {n_wires * K}), got {tuple(x.shape)}")
+    if tuple(weights.shape) != (S, 3, n_wires):
+        raise ValueError(f"weights must be (S,3,n) = ({S},3,{n_wires}), got {tuple(weights.shape)}")
+    if ham_diag is not None:
+        if ham_diag.numel() != (1 << n_wires):
+            raise ValueError(f"ham_diag must have 2**n = {1 << n_wires} entries, got {ham_diag.numel()}")
+
+
+def _rowmajor(x):
+    """Rows contiguous (stride(1) == 1, or a single column); returns (tensor, row_stride)."""
+    if x.shape[0] <= 1 or x.shape[1] == 0:
+        x = x.contiguous()
+        return x, max(int(x.shape[1]), 1)
+    if x.stride(1) != 1 or x.stride(0) < x.shape[1]:
+        x = x.contiguous()
+    return x, int(x.stride(0))
+
+
+def _workspace(B, n, depth, dtype_code, need_grad, device):
+    lib = _lib.load()
+    nbytes = lib.qon_workspace_bytes(B, n, len(depth), depth, dtype_code, int(need_grad))
+    if nbytes == 0:
+        raise RuntimeError(f"qon_workspace_bytes failed: {_lib.last_error()}")
+    return torch.empty(nbytes, dtype=torch.uint8, device=device), nbytes
+
+
+@torch.library.custom_op("quanonet::hea_expval", mutates_args=())
+def hea_expval(x: torch.Tensor, weights: torch.Tensor, n_wires: int, depth_per_block: List[int],
+               ham_diag: Optional[torch.Tensor], diag_order: int, ham_offset: float, ham_coeff: float,
+               ham_kind: int) -> torch.Tensor:
+    _check_inputs(x, weights, n_wires, depth_per_block, ham_diag)
+    lib = _lib.load()
+    code = _DTYPES[x.dtype]
+    B = x.shape[0]
+    out = torch.empty((B, 1), dtype=x.dtype, device=x.device)
+    if B == 0:
+        return out
+    with torch.cuda.device(x.device):
+        xc, ldx = _rowmajor(x)
+        wc = weights.contiguous()
+        hd = None if ham_diag is None else ham_diag.to(dtype=x.dtype, device=x.device).contiguous()
+        depth = _lib.int_array(depth_per_block)
+        ws, nbytes = _workspace(B, n_wires, depth, code, False, x.device)
+        stream = torch.cuda.current_stream(x.device).cuda_stream
+        rc = lib.qon_hea_forward(xc.data_ptr(), ldx, wc.data_ptr(), out.data_ptr(), B, n_wires, len(depth_per_block),
+                                 depth, None if hd is None else hd.data_ptr(), diag_order, ham_offset, ham_coeff,
+                                 ham_kind, code, ws.data_ptr(), nbytes, stream)
+        _lib.check(rc, "qon_hea_forward")
+    return out
+
+
+@hea_expval.register_fake
+def _(x, weights, n_wires, depth_per_block, ham_diag, diag_order, ham_offset, ham_coeff, ham_kind):
+    return x.new_empty((x.shape[0], 1))
+
+
+@torch.library.custom_op("quanonet::hea_expval_backward", mutates_args=())
+def hea_expval_backward(grad_out: torch.Tensor, x: torch.Tensor, weights: torch.Tensor, n_wires: int,
+                        depth_per_block: List[int], ham_diag: Optional[torch.Tensor], diag_order: int,
+                        ham_offset: float, ham_coeff: float, ham_kind: int,
+                        need_grad_x: bool) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """One fused forward + adjoint-backward pass.  Returns (out (B,1), grad_x (B,n*K) or empty, grad_w)."""
+    _check_inputs(x, weights, n_wires, depth_per_block, ham_diag)
+    lib = _lib.load()
+    code = _DTYPES[x.dtype]
+    B = x.shape[0]
+    out = torch.empty((B, 1), dtype=x.dtype, device=x.device)
+    grad_w = torch.empty_like(weights, memory_format=torch.contiguous_format)
+    grad_x = torch.empty((B, x.shape[1]) if need_grad_x else (0,), dtype=x.dtype, device=x.device)
+    with torch.cuda.device(x.device):
+        xc, ldx = _rowmajor(x)
+        wc = weights.contiguous()
+        g = grad_out.to(dtype=x.dtype).reshape(-1).contiguous()
+        if g.numel() != B:
+            raise ValueError(f"grad_out must have B = {B} elements, got {g.numel()}")
+        hd = None if ham_diag is None else ham_diag.to(dtype=x.dtype, device=x.device).contiguous()
+        depth = _lib.int_array(depth_per_block)
+        ws, nbytes = _workspace(B, n_wires, depth, code, True, x.device)
+        stream = torch.cuda.current_stream(x.device).cuda_stream
+        rc = lib.qon_hea_forward_backward(
+            xc.data_ptr(), ldx, wc.data_ptr(), g.data_ptr(), out.data_ptr(),
+            grad_x.data_ptr() if need_grad_x else None, max(int(x.shape[1]), 1), grad_w.data_ptr(),
+            B, n_wires, len(depth_per_block), depth, None if hd is None else hd.data_ptr(), diag_order,
+            ham_offset, ham_coeff, ham_kind, code, ws.data_ptr(), nbytes, stream)
+        _lib.check(rc, "qon_hea_forward_backward")
+    return out, grad_x, grad_w
+
+
+@hea_expval_backward.register_fake
+def _(grad_out, x, weights, n_wires, depth_per_block, ham_diag, diag_order, ham_offset, ham_coeff, ham_kind,
+      need_grad_x):
+    gx = x.new_empty(x.shape if need_grad_x else (0,))
+    return x.new_empty((x.shape[0], 1)), gx, torch.empty_like(weights)
+
+
+def _setup_context(ctx, inputs, output):
+    x, weights, n_wires, depth, ham_diag, diag_order, off, coeff, kind = inputs
+    ctx.save_for_backward(x, weights, ham_diag if ham_diag is not None else x.new_empty(0))
+    ctx.has_diag = ham_diag is not None
+    ctx.cfg = (n_wires, list(depth), diag_order, off, coeff, kind)
+
+
+def _backward(ctx, grad_out):
+    x, weights, hd = ctx.saved_tensors
+    n_wires, depth, diag_order, off, coeff, kind = ctx.cfg
+    need_gx = ctx.needs_input_grad[0]
+    _, gx, gw = hea_expval_backward(grad_out.contiguous(), x, weights, n_wires, depth,
+                                    hd if ctx.has_diag else None, diag_order, off, coeff, kind, need_gx)
+    return (gx if need_gx else None), (gw if ctx.needs_input_grad[1] else None), None, None, None, None, None, None, None
+
+
+hea_expval.register_autograd(_backward, setup_context=_setup_context)
+
+
+def fp32_peak_tflops(iters: int = 2000) -> float:
+    """Measured FFMA throughput of the current device (TFLOP/s) — the '% of FP32 peak' denominator."""
+    lib = _lib.load()
+    v = lib.qon_measure_fp32_peak_tflops(int(iters), torch.cuda.current_stream().cuda_stream)
+    if v <= 0:
+        raise RuntimeError(f"FP32 peak probe failed: {_lib.last_error()}")
+    return float(v)
+
+
+def plan_tier(B: int, n: int, dtype=torch.float32, need_grad=True):
+    """(tier, lanes_log2) the library would use: tier 0 register, 1 shared memory, 2 HBM-streamed."""
+    import ctypes
+    lib = _lib.load()
+    lq = ctypes.c_int(-1)
+    t = lib.qon_plan_tier(B, n, _DTYPES[dtype], int(need_grad), ctypes.byref(lq))
+    if t < 0:
+        raise RuntimeError(_lib.last_error())
+    return t, lq.value
