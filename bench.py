@@ -1,0 +1,391 @@
+#!/usr/bin/env python
+"""bench.py — QuanONet Q5 fwd+adjoint-grad training throughput on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--batch B]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+           --master-port P bench.py --gpus N --steps K --warmup W
+
+Workload (BASELINE.json configs[1], SURVEY §8d "C2"): Advection-shaped QuanONet, n = 5 qubits,
+net (40,2,20,2), branch_in 100, trunk_in 2, trainable frequency layers; synthetic batch of 1M
+(function, query-point) samples PER GPU (weak scaling: global batch = N x 1M); one step = one full
+training step over the batch: frequency layers -> fused forward + MSE + adjoint-backward kernel ->
+chain rule to the frequency parameters -> all-reduce of the flat 2,401-float gradient (N > 1) ->
+Adam update.  Prints ONE JSON line (rank 0).
+
+`value`   : whole-job samples/s with the batch resident in HBM (CUDA events, max over ranks).
+`e2e`     : the same step fed from pinned HOST memory every step (H2D of branch/trunk/target inside
+            the timed region, double-buffered on a copy stream) plus a D2H read of the loss.
+`roofline`: the dominant kernel (hea_reg_kernel, fwd+grad) against the FP32 FFMA peak measured on this
+            GPU in the same run (MEASURED_PEAKS.json has no FP32 entry); algorithmic flops per sample
+            = 22*N*G + 7*N = 1,478,624.
+`cpu_baseline` / `--impl reference`: the TorchQuantum-faithful complex64 restatement of the
+            reference path (oracle/tq_faithful.py; torchquantum itself is not installable here)
+            timed on the host cores, on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+N_QUBITS = 5
+NET = (40, 2, 20, 2)          # branch_depth, branch_linear_depth, trunk_depth, trunk_linear_depth
+BRANCH_IN, TRUNK_IN = 100, 2
+METRIC = "quanonet_q5_fwd_adjoint_grad_samples_per_s"
+WORKLOAD = "Advection-shaped QuanONet Net40-2-20-2 Q5 (TF), MSE training step, synthetic"
+
+
+def alg_flops(n=N_QUBITS, net=NET):
+    N = 1 << n
+    K = net[0] + net[2]
+    S = net[0] * net[1] + net[2] * net[3]
+    G = n * K + 3 * n * S
+    return 6 * N * G + 5 * N, 22 * N * G + 7 * N
+
+
+def make_model(device, seed=0):
+    from quanonet_b200.core.models_pt import QuanONetPT
+    torch.manual_seed(seed)
+    m = QuanONetPT(N_QUBITS, BRANCH_IN, TRUNK_IN, NET, scale_coeff=0.1, if_trainable_freq=True,
+                   ham_bound=(-5.0, 5.0))
+    with torch.no_grad():   # MindSpore initialises the frequency bias U(-pi, pi) (core/layers.py:24-27)
+        m.branch_freq.bias.uniform_(-np.pi, np.pi)
+        m.trunk_freq.bias.uniform_(-np.pi, np.pi)
+    return m.to(device)
+
+
+def synth_batch(B, seed, device=None, pin=False):
+    g = torch.Generator().manual_seed(seed)
+    branch = torch.randn(B, BRANCH_IN, generator=g)
+    trunk = torch.rand(B, TRUNK_IN, generator=g)
+    y = torch.randn(B, 1, generator=g)
+    if device is not None:
+        return branch.to(device), trunk.to(device), y.to(device)
+    if pin:
+        return branch.pin_memory(), trunk.pin_memory(), y.pin_memory()
+    return branch, trunk, y
+
+
+# ---------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """Samples SM clock and throttle reasons of one GPU every 200 ms (NVML) while active."""
+    REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake_slowdown"}
+
+    def __init__(self, device_index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            try:
+                uuid = torch.cuda.get_device_properties(device_index).uuid
+                self.h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + str(uuid)).encode())
+            except Exception:
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nv = None
+
+    def _loop(self):
+        while not self._stop.is_set():
+            try:
+                self.samples.append(int(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)))
+                try:
+                    bits = int(self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                except Exception:
+                    bits = int(self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                for bit, name in self.REASONS.items():
+                    if bits & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self._thread = threading.Thread(target=self._loop, daemon=True)
+            self._thread.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join(timeout=2)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": 0}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ---------------------------------------------------------------------------------- CPU reference arm
+def cpu_reference_step_fn(B, threads=None):
+    """One training step of the reference path on the host: frequency layers, TorchQuantum-faithful
+    complex64 circuit with autograd (oracle/tq_faithful.py), MSELoss, backward, Adam."""
+    from oracle.tq_faithful import tq_forward
+    if threads:
+        torch.set_num_threads(threads)
+    model = make_model("cpu")
+    blocks = model.quantum_layer.block_configs
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+    branch, trunk, y = synth_batch(B, seed=1)
+
+    def step():
+        opt.zero_grad()
+        x = torch.cat([model.trunk_freq(trunk), model.branch_freq(branch)], dim=1)
+        pred = tq_forward(x, model.quantum_layer.ansatz_weights, N_QUBITS, blocks, 0.0, 1.0) + model.bias
+        loss = torch.nn.functional.mse_loss(pred, y)
+        loss.backward()
+        opt.step()
+        return float(loss.detach())
+
+    return step
+
+
+def time_cpu_reference(budget_s, steps=None, warmup=0):
+    """Returns (samples/s, ms/step, B, steps) of the CPU reference on a bounded sample."""
+    t0 = time.perf_counter()
+    cpu_reference_step_fn(64)()                      # calibration (also pages torch in)
+    rate = 64 / max(time.perf_counter() - t0, 1e-3)
+    n_steps = steps if steps is not None else 3
+    B = int(min(1000, max(32, rate * 2.5 * budget_s / (n_steps + warmup))))   # larger batches run ~2.5x faster/sample
+    step = cpu_reference_step_fn(B)
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(n_steps):
+        step()
+    dt = time.perf_counter() - t0
+    return B * n_steps / dt, dt / n_steps * 1e3, B, n_steps
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sps, ms, B, n_steps = time_cpu_reference(budget_s=120.0, steps=args.steps, warmup=args.warmup)
+    cores = torch.get_num_threads()
+    line = {
+        "impl": "reference", "metric": METRIC, "value": sps, "unit": "samples/s", "n_gpus": args.gpus,
+        "steps": n_steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "batch_per_step": B, "note": "bounded sample of the 1M-sample batch"},
+        "cpu_baseline": {"value": sps, "unit": "samples/s", "cores": cores, "kind": "port",
+                         "sample": f"{n_steps} training steps of {B} samples (TorchQuantum-faithful complex64 "
+                                   f"restatement with autograd; torchquantum is not installable offline)"},
+        "e2e": {"value": sps, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------- B200 arm
+def run_b200(args):
+    import torch.distributed as dist
+    from quanonet_b200 import _lib
+    from quanonet_b200.ops import fp32_peak_tflops, hea_expval
+    from quanonet_b200.train import DataParallelTrainer, _default_kernel
+
+    _lib.load()                                   # fail loudly if the CUDA library is missing
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device (no CPU fallback for the B200 arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B = args.batch
+    K, W = args.steps, max(args.warmup, 3)
+    f_fwd, f_all = alg_flops()
+
+    model = make_model(dev, seed=0)
+    kernel_events = []
+
+    def timed_kernel(*a):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        r = _default_kernel(*a)
+        e1.record()
+        kernel_events.append((e0, e1))
+        return r
+
+    trainer = DataParallelTrainer(model, lr=1e-3, optimizer="adam", kernel_fn=timed_kernel)
+    branch, trunk, y = synth_batch(B, seed=100 + rank, device=dev)
+    peak = fp32_peak_tflops(4000) if rank == 0 else None
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident timing (value)
+    for _ in range(W):
+        trainer.step((branch, trunk), y)
+    kernel_events.clear()
+    sync_all()
+    sampler = ClockSampler(local)
+    with sampler:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(K):
+            loss = trainer.step((branch, trunk), y)
+        e1.record()
+        sync_all()
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    ms_step = ms_total / K
+    value = world * B * K / (ms_total * 1e-3)
+    kern_ms = float(np.mean([a.elapsed_time(b) for a, b in kernel_events]))
+    final_loss = float(loss)
+
+    # ---- forward-only throughput (inference path), same batch
+    with torch.no_grad():
+        x_enc = torch.cat([model.trunk_freq(trunk), model.branch_freq(branch)], dim=1)
+        q = model.quantum_layer
+        depths = [d for _, d in q.block_configs]
+        for _ in range(2):
+            hea_expval(x_enc, q.ansatz_weights, N_QUBITS, depths, None, 0, q.ham_offset, q.ham_coeff, 0)
+        torch.cuda.synchronize()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        for _ in range(5):
+            hea_expval(x_enc, q.ansatz_weights, N_QUBITS, depths, None, 0, q.ham_offset, q.ham_coeff, 0)
+        f1.record()
+        torch.cuda.synchronize()
+        fwd_ms = f0.elapsed_time(f1) / 5
+        del x_enc
+
+    # ---- end to end from pinned host memory (e2e)
+    host = [synth_batch(B, seed=200 + rank + 7 * i, pin=True) for i in range(2)]
+    dbuf = [tuple(torch.empty_like(t, device=dev) for t in host[0]) for _ in range(2)]
+    copy_stream = torch.cuda.Stream(device=dev)
+    ready = [torch.cuda.Event() for _ in range(2)]
+    consumed = [torch.cuda.Event() for _ in range(2)]
+    loss_host = torch.empty(1, dtype=torch.float32).pin_memory()
+
+    def enqueue_copy(i):
+        slot = i % 2
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[slot])
+            for d, h in zip(dbuf[slot], host[slot]):
+                d.copy_(h, non_blocking=True)
+            ready[slot].record(copy_stream)
+
+    def e2e_loop(n_steps):
+        cur = torch.cuda.current_stream()
+        for c in consumed:
+            c.record(cur)
+        enqueue_copy(0)
+        last = None
+        for i in range(n_steps):
+            if i + 1 < n_steps:
+                enqueue_copy(i + 1)
+            slot = i % 2
+            cur.wait_event(ready[slot])
+            b_, t_, y_ = dbuf[slot]
+            l = trainer.step((b_, t_), y_)
+            consumed[slot].record(cur)
+            loss_host.copy_(l.reshape(1).float(), non_blocking=True)     # D2H read of the step's loss
+            last = l
+        torch.cuda.synchronize()
+        return float(loss_host[0])
+
+    e2e_loop(3)
+    sync_all()
+    t0 = time.perf_counter()
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g0.record()
+    e2e_loop(K)
+    g1.record()
+    sync_all()
+    e2e_ms = max_over_ranks(max(g0.elapsed_time(g1), (time.perf_counter() - t0) * 1e3 * 0.0))
+    e2e_value = world * B * K / (e2e_ms * 1e-3)
+    h2d = sum(t.numel() * t.element_size() for t in host[0])
+
+    cpu_base = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        sps, ms, Bc, ns = time_cpu_reference(budget_s=20.0)
+        cpu_base = {"value": sps, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
+                    "sample": f"{ns} training steps of {Bc} samples of the same workload "
+                              f"(TorchQuantum-faithful complex64 restatement, autograd backward)"}
+
+    if rank == 0:
+        achieved = f_all * B / (kern_ms * 1e-3) / 1e12
+        nominal = 148 * 128 * 2 * 1.965e9 / 1e12
+        traffic = None
+        tf = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tf):
+            try:
+                traffic = json.load(open(tf)).get("hea_reg_kernel_fwd_grad_bytes_per_launch")
+            except Exception:
+                traffic = None
+        line = {
+            "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "num_qubits": N_QUBITS, "net_size": list(NET),
+                       "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world}",
+                       "l2_policy": "inputs larger than L2: per-step inputs 412 MB + 1.2 GB encoding matrix vs 126 MB L2",
+                       "step": "freq layers + fused fwd/MSE/adjoint-grad kernel + chain rule + all-reduce + Adam"},
+            "clocks": sampler.summary(),
+            "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                    "ms_per_step": e2e_ms / K},
+            "gpu_launches": 3 * K,
+            "roofline": {"bound": "fp32", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                         "frac": achieved / peak if peak else None, "traffic": traffic,
+                         "kernel": "hea_reg_kernel<float,5,0,grad> (+prep, finalize)", "kernel_ms": kern_ms,
+                         "flops_per_sample": f_all, "peak_source": "FFMA probe measured on this GPU in this run "
+                         "(MEASURED_PEAKS.json has no FP32 entry)", "peak_nominal": nominal,
+                         "frac_of_nominal": achieved / nominal},
+            "forward_only": {"value": B / (fwd_ms * 1e-3), "unit": "samples/s",
+                             "tflops": f_fwd * B / (fwd_ms * 1e-3) / 1e12},
+            "final_loss": final_loss,
+        }
+        if cpu_base is not None:
+            line["cpu_baseline"] = cpu_base
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=1_000_000, help="samples per GPU per step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -93,6 +93,21 @@ int qon_hea_forward_backward(const void* x, int64_t ldx, const void* w, const vo
                              const void* ham_diag, int diag_order, double ham_offset, double ham_coeff,
                              int ham_kind, int dtype, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Training-step variant: the upstream gradient of the reference's MSE loss
+ * (loss_fn = nn.MSELoss(), solvers/solver_pt.py:66,233-235) is formed inside the kernel,
+ *     g[b] = grad_scale * (out[b] + bias - target[b])        (grad_scale = 2 / B_global for a mean),
+ * so forward, loss gradient and adjoint backward are ONE pass over the batch.
+ *   target           device, (B,)
+ *   bias             device scalar (the model's `bias` parameter, core/models_pt.py:151,166) or NULL (= 0)
+ *   out              device, (B,)   expectation values WITHOUT bias
+ *   grad_out_written device, (B,)   receives g[b]  (sum_b g[b] = dL/dbias; loss = sum (g/grad_scale)^2 / B)
+ * Other arguments as qon_hea_forward_backward. */
+int qon_hea_mse_forward_backward(const void* x, int64_t ldx, const void* w, const void* target, const void* bias,
+                                 double grad_scale, void* out, void* grad_out_written, void* grad_x, int64_t ldgx,
+                                 void* grad_w, int64_t B, int n, int K, const int* depth_per_block,
+                                 const void* ham_diag, int diag_order, double ham_offset, double ham_coeff,
+                                 int ham_kind, int dtype, void* workspace, size_t workspace_bytes, void* stream);
+
 /* Which kernel tier a problem maps to on the current device: 0 = register tier (state in registers,
  * 2^lanes_log2 lanes per sample), 1 = shared-memory tier, 2 = HBM-streamed tier; -1 = unsupported. */
 int qon_plan_tier(int64_t B, int n, int dtype, int need_grad, int* lanes_log2);

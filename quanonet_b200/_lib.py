@@ -24,6 +24,7 @@ EXPORTED_SYMBOLS = (
     "qon_workspace_bytes",
     "qon_hea_forward",
     "qon_hea_forward_backward",
+    "qon_hea_mse_forward_backward",
     "qon_plan_tier",
     "qon_measure_fp32_peak_tflops",
 )
@@ -51,6 +52,9 @@ def _declare(lib):
     lib.qon_hea_forward_backward.restype = i32
     lib.qon_hea_forward_backward.argtypes = [vp, i64, vp, vp, vp, vp, i64, vp, i64, i32, i32, ip,
                                              vp, i32, dbl, dbl, i32, i32, vp, sz, vp]
+    lib.qon_hea_mse_forward_backward.restype = i32
+    lib.qon_hea_mse_forward_backward.argtypes = [vp, i64, vp, vp, vp, dbl, vp, vp, vp, i64, vp, i64, i32, i32, ip,
+                                                 vp, i32, dbl, dbl, i32, i32, vp, sz, vp]
     lib.qon_plan_tier.restype = i32
     lib.qon_plan_tier.argtypes = [i64, i32, i32, i32, ip]
     lib.qon_measure_fp32_peak_tflops.restype = dbl

@@ -25,7 +25,12 @@ struct HeaParams {
     int64_t ldx;
     int64_t B;
     T* out;              // (B,) expectation values
-    const T* gout;       // (B,) upstream gradient dL/dout          [grad only]
+    const T* gout;       // (B,) upstream gradient dL/dout          [grad only; unused when target != null]
+    const T* target;     // (B,) regression target y: the kernel forms the MSE upstream gradient itself,
+                         //      g_b = gscale * (out_b + bias - y_b), and writes it to gbuf   [optional]
+    const T* bias;       // device scalar added to out inside the residual (may be null = 0)
+    T* gbuf;             // (B,) where g_b is written when target != null
+    T gscale;
     T* gx;               // (B, n*K) dL/dx, row stride ldgx; may be null [grad only]
     int64_t ldgx;
     const Vec4<T>* ucoef;

@@ -138,8 +138,7 @@ __global__ void hea_generic_kernel(const HeaParams<T> p, const int n, const int 
                 g_ring(pr, pi, N, n, false);
             }
         }
-        // ---- expectation: e = sum_k Re(conj(psi_k) (H psi)_k); lam = g * H psi
-        const T g = GRAD ? p.gout[b] : T(0);
+        // ---- expectation: e = sum_k Re(conj(psi_k) (H psi)_k); lam = H psi (scaled by g below)
         T e = 0;
         for (int64_t i = threadIdx.x; i < N; i += blockDim.x) {
             T hr, hi;
@@ -158,12 +157,21 @@ __global__ void hea_generic_kernel(const HeaParams<T> p, const int n, const int 
                 }
             }
             e = fma_(pr[i], hr, e); e = fma_(pi[i], hi, e);
-            if (GRAD) { lr[i] = g * hr; li[i] = g * hi; }
+            if (GRAD) { lr[i] = hr; li[i] = hi; }
         }
         e = block_sum(e, red);
         if (threadIdx.x == 0) p.out[b] = e;
         __syncthreads();
         if constexpr (GRAD) {
+            T g;
+            if (p.target) {
+                g = p.gscale * (e + (p.bias ? p.bias[0] : T(0)) - p.target[b]);
+                if (threadIdx.x == 0) p.gbuf[b] = g;
+            } else {
+                g = p.gout[b];
+            }
+            for (int64_t i = threadIdx.x; i < N; i += blockDim.x) { lr[i] *= g; li[i] *= g; }
+            __syncthreads();
             // ---- reverse sweep
             T* gxrow = NEED_GX ? p.gx + b * p.ldgx : nullptr;
             s = p.S;

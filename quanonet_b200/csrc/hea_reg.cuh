@@ -2,6 +2,12 @@
 //
 //   LQ == 0 : one THREAD owns a whole sample (n <= 5 in fp32, n <= 4 in fp64).  Every gate is
 //             in-lane FMAs; the CNOT ring is a compile-time register renaming (zero instructions).
+//             In fp32 each complex amplitude is one aligned 64-bit register pair and every gate is
+//             issued as Blackwell packed-FP32 FFMA2 (fma.rn.f32x2): ptxas folds the (re,im) swap,
+//             the per-half sign and the scalar-coefficient broadcast into FFMA2 operand modifiers
+//             (.LO_HI / .NP / .F32), so a complex multiply-accumulate is 2 instructions, not 4.
+//             Half the instruction count halves the SASS footprint (the scalar version ran at a
+//             77 % instruction-cache hit rate, see profiles/) and frees issue slots.
 //   LQ  > 0 : gates on the low NL qubits stay in-lane; the top LQ qubits pair lanes with
 //             __shfl_xor; CNOTs become renames / predicated selects / lane permutations.
 //
@@ -18,10 +24,12 @@
 // Gate fusion: RY(c)RZ(b)RY(a) is one SU(2) matrix [[al,-conj(be)],[be,conj(al)]] from the prep
 // table; in the first sublayer of a block the per-sample RX(theta) is folded in
 // (al' = al*c + i s conj(be), be' = be*c - i s conj(al)), so a block of depth d costs d*n fused
-// gates of 16 FP32 instructions per amplitude pair instead of (3d+1)*n gates of 8.
+// gates instead of (3d+1)*n.
 #pragma once
+#include <type_traits>
 #include <utility>
 #include "hea_common.cuh"
+#include "ffma2.cuh"
 
 namespace qon {
 
@@ -41,12 +49,21 @@ __device__ __forceinline__ void static_for(F&& f) {
 template <typename T> __device__ __forceinline__ T shfl_xor_(T v, int m) { return __shfl_xor_sync(QON_FULL, v, m); }
 template <typename T> __device__ __forceinline__ T shfl_idx_(T v, int l) { return __shfl_sync(QON_FULL, v, l); }
 
-// ------------------------------------------------------------------------------------------------
-// one fused SU(2) gate on qubit Q;  DAG applies the inverse
-// ------------------------------------------------------------------------------------------------
-template <typename T, int NL, int Q, bool DAG>
-__device__ __forceinline__ void apply_u(T (&re)[1 << NL], T (&im)[1 << NL], T ar, T ai, T br, T bi, int lane) {
+// =================================================================================================
+// Scalar state (fp64, and fp32 when lanes share a sample): separate re / im register arrays
+// =================================================================================================
+template <typename T, int NL_>
+struct ScalarState {
+    static constexpr int NL = NL_;
+    static constexpr int NA = 1 << NL_;
+    T re[NA], im[NA];
+};
+
+template <int Q, bool DAG, typename T, int NL>
+__device__ __forceinline__ void apply_u(ScalarState<T, NL>& st, T ar, T ai, T br, T bi, int lane) {
     constexpr int NA = 1 << NL;
+    T(&re)[NA] = st.re;
+    T(&im)[NA] = st.im;
     if constexpr (Q < NL) {
         constexpr int bit = 1 << Q;
 #pragma unroll
@@ -82,13 +99,15 @@ __device__ __forceinline__ void apply_u(T (&re)[1 << NL], T (&im)[1 << NL], T ar
     }
 }
 
-// ------------------------------------------------------------------------------------------------
-// reverse-sweep group: Pauli moments of (lam, psi) on qubit Q, then un-apply the gate on both
-// ------------------------------------------------------------------------------------------------
-template <typename T, int NL, int Q>
-__device__ __forceinline__ void bwd_group(T (&pr)[1 << NL], T (&pi)[1 << NL], T (&lr)[1 << NL], T (&li)[1 << NL],
-                                          T ar, T ai, T br, T bi, int lane, T& mX, T& mY, T& mZ) {
+// Pauli moments of (lam, psi) on qubit Q (state AFTER the gate), then un-apply the gate on both.
+template <int Q, typename T, int NL>
+__device__ __forceinline__ void bwd_group(ScalarState<T, NL>& ps, ScalarState<T, NL>& lm, T ar, T ai, T br, T bi,
+                                          int lane, T& mX, T& mY, T& mZ) {
     constexpr int NA = 1 << NL;
+    T(&pr)[NA] = ps.re;
+    T(&pi)[NA] = ps.im;
+    T(&lr)[NA] = lm.re;
+    T(&li)[NA] = lm.im;
     if constexpr (Q < NL) {
         constexpr int bit = 1 << Q;
         T x = 0, y = 0, z = 0;
@@ -107,8 +126,8 @@ __device__ __forceinline__ void bwd_group(T (&pr)[1 << NL], T (&pi)[1 << NL], T 
             z = fma_(-lr[j], pi[j], z); z = fma_(li[j], pr[j], z);
         }
         mX = x; mY = y; mZ = z;
-        apply_u<T, NL, Q, true>(pr, pi, ar, ai, br, bi, lane);
-        apply_u<T, NL, Q, true>(lr, li, ar, ai, br, bi, lane);
+        apply_u<Q, true>(ps, ar, ai, br, bi, lane);
+        apply_u<Q, true>(lm, ar, ai, br, bi, lane);
     } else {
         constexpr int lb = Q - NL;
         const bool hi = (lane >> lb) & 1;
@@ -132,12 +151,11 @@ __device__ __forceinline__ void bwd_group(T (&pr)[1 << NL], T (&pi)[1 << NL], T 
     }
 }
 
-// ------------------------------------------------------------------------------------------------
-// CNOT(control C, target TG) and the ring
-// ------------------------------------------------------------------------------------------------
-template <typename T, int NL, int C, int TG>
-__device__ __forceinline__ void cnot(T (&re)[1 << NL], T (&im)[1 << NL], int lane) {
+template <int C, int TG, typename T, int NL>
+__device__ __forceinline__ void cnot(ScalarState<T, NL>& st, int lane) {
     constexpr int NA = 1 << NL;
+    T(&re)[NA] = st.re;
+    T(&im)[NA] = st.im;
     if constexpr (C < NL && TG < NL) {          // pure register renaming
 #pragma unroll
         for (int i = 0; i < NA; ++i) {
@@ -174,23 +192,31 @@ __device__ __forceinline__ void cnot(T (&re)[1 << NL], T (&im)[1 << NL], int lan
     }
 }
 
-template <typename T, int NL, int LQ, bool REVERSE>
-__device__ __forceinline__ void cnot_ring(T (&re)[1 << NL], T (&im)[1 << NL], int lane) {
-    constexpr int NQ = NL + LQ;
-    if constexpr (NQ > 1) {
-        static_for<NQ>([&](auto I) {
-            constexpr int i = REVERSE ? (NQ - 1 - decltype(I)::value) : decltype(I)::value;
-            cnot<T, NL, (i + 1) % NQ, i>(re, im, lane);
-        });
-    }
+template <typename T, int NL>
+__device__ __forceinline__ void init_zero_state(ScalarState<T, NL>& st, bool owner) {
+#pragma unroll
+    for (int i = 0; i < (1 << NL); ++i) { st.re[i] = 0; st.im[i] = 0; }
+    st.re[0] = owner ? T(1) : T(0);
 }
 
-// ------------------------------------------------------------------------------------------------
-// H psi  (pauli 0: diagonal table, 1: offset + coeff sum_q X_q, 2: offset + coeff sum_q Y_q)
-// ------------------------------------------------------------------------------------------------
-template <typename T, int NL, int LQ>
-__device__ __forceinline__ void apply_ham(const HeaParams<T>& p, const T (&pr)[1 << NL], const T (&pi)[1 << NL],
-                                          T (&lr)[1 << NL], T (&li)[1 << NL], int lane) {
+template <typename T, int NL>
+__device__ __forceinline__ void scale_state(ScalarState<T, NL>& st, T g) {
+#pragma unroll
+    for (int i = 0; i < (1 << NL); ++i) { st.re[i] *= g; st.im[i] *= g; }
+}
+
+template <typename T, int NL>
+__device__ __forceinline__ T real_dot(const ScalarState<T, NL>& a, const ScalarState<T, NL>& b) {
+    T e = 0;
+#pragma unroll
+    for (int i = 0; i < (1 << NL); ++i) { e = fma_(a.re[i], b.re[i], e); e = fma_(a.im[i], b.im[i], e); }
+    return e;
+}
+
+// lam = H psi  (pauli 0: diagonal table, 1: offset + coeff sum_q X_q, 2: offset + coeff sum_q Y_q)
+template <int LQ, typename T, int NL>
+__device__ __forceinline__ void apply_ham(const HeaParams<T>& p, const ScalarState<T, NL>& ps, ScalarState<T, NL>& lm,
+                                          int lane) {
     constexpr int NA = 1 << NL;
     constexpr int NQ = NL + LQ;
     const int sub = lane & ((1 << LQ) - 1);
@@ -198,14 +224,14 @@ __device__ __forceinline__ void apply_ham(const HeaParams<T>& p, const T (&pr)[1
 #pragma unroll
         for (int i = 0; i < NA; ++i) {
             const T d = __ldg(p.hdiag + ((sub << NL) | i));
-            lr[i] = d * pr[i];
-            li[i] = d * pi[i];
+            lm.re[i] = d * ps.re[i];
+            lm.im[i] = d * ps.im[i];
         }
         return;
     }
     const bool isY = p.pauli == 2;
 #pragma unroll
-    for (int i = 0; i < NA; ++i) { lr[i] = p.offset * pr[i]; li[i] = p.offset * pi[i]; }
+    for (int i = 0; i < NA; ++i) { lm.re[i] = p.offset * ps.re[i]; lm.im[i] = p.offset * ps.im[i]; }
     static_for<NQ>([&](auto Qc) {
         constexpr int Q = decltype(Qc)::value;
 #pragma unroll
@@ -213,19 +239,185 @@ __device__ __forceinline__ void apply_ham(const HeaParams<T>& p, const T (&pr)[1
             T fr, fi;   // flipped amplitude psi_{k ^ bit}
             bool one;   // bit Q of this amplitude's index
             if constexpr (Q < NL) {
-                fr = pr[i ^ (1 << Q)]; fi = pi[i ^ (1 << Q)]; one = (i >> Q) & 1;
+                fr = ps.re[i ^ (1 << Q)]; fi = ps.im[i ^ (1 << Q)]; one = (i >> Q) & 1;
             } else {
-                fr = shfl_xor_(pr[i], 1 << (Q - NL)); fi = shfl_xor_(pi[i], 1 << (Q - NL));
+                fr = shfl_xor_(ps.re[i], 1 << (Q - NL)); fi = shfl_xor_(ps.im[i], 1 << (Q - NL));
                 one = (lane >> (Q - NL)) & 1;
             }
             if (!isY) {
-                lr[i] = fma_(p.coeff, fr, lr[i]); li[i] = fma_(p.coeff, fi, li[i]);
+                lm.re[i] = fma_(p.coeff, fr, lm.re[i]); lm.im[i] = fma_(p.coeff, fi, lm.im[i]);
             } else {     // (Y psi)_k = +i psi_flip if bit set else -i psi_flip ; i(a+ib) = -b + ia
                 const T sg = one ? p.coeff : -p.coeff;
-                lr[i] = fma_(-sg, fi, lr[i]); li[i] = fma_(sg, fr, li[i]);
+                lm.re[i] = fma_(-sg, fi, lm.re[i]); lm.im[i] = fma_(sg, fr, lm.im[i]);
             }
         }
     });
+}
+
+// =================================================================================================
+// Packed state (fp32, one thread per sample): amplitude k = one 64-bit register pair (re, im); all
+// gate arithmetic is FFMA2 / FMUL2 through the operand-pattern wrappers of ffma2.cuh.
+// =================================================================================================
+template <int NL_>
+struct PackedState {
+    static constexpr int NL = NL_;
+    static constexpr int NA = 1 << NL_;
+    u64 a[NA];
+};
+
+template <int Q, bool DAG, int NL>
+__device__ __forceinline__ void apply_u(PackedState<NL>& st, float ar, float ai, float br, float bi, int) {
+    constexpr int NA = 1 << NL;
+    constexpr int bit = 1 << Q;
+    static_assert(Q < NL, "packed state is single-lane");
+#pragma unroll
+    for (int i = 0; i < NA; ++i) {
+        if (i & bit) continue;
+        const int j = i | bit;
+        const u64 x0 = st.a[i], x1 = st.a[j];
+        u64 n0, n1;
+        if constexpr (!DAG) {
+            // a0' = al a0 - conj(be) a1 = ar x0 + ai (i x0) - br x1 + bi (i x1)
+            n0 = mul2<0>(ar, x0);
+            n0 = fma2<2>(ai, x0, n0);
+            n0 = fma2<6>(br, x1, n0);
+            n0 = fma2<2>(bi, x1, n0);
+            // a1' = be a0 + conj(al) a1 = br x0 + bi (i x0) + ar x1 + ai (-i x1)
+            n1 = mul2<0>(br, x0);
+            n1 = fma2<2>(bi, x0, n1);
+            n1 = fma2<0>(ar, x1, n1);
+            n1 = fma2<3>(ai, x1, n1);
+        } else {
+            // a0' = conj(al) a0 + conj(be) a1 = ar x0 + ai (-i x0) + br x1 + bi (-i x1)
+            n0 = mul2<0>(ar, x0);
+            n0 = fma2<3>(ai, x0, n0);
+            n0 = fma2<0>(br, x1, n0);
+            n0 = fma2<3>(bi, x1, n0);
+            // a1' = -be a0 + al a1 = -br x0 + bi (-i x0) + ar x1 + ai (i x1)
+            n1 = mul2<6>(br, x0);
+            n1 = fma2<3>(bi, x0, n1);
+            n1 = fma2<0>(ar, x1, n1);
+            n1 = fma2<2>(ai, x1, n1);
+        }
+        st.a[i] = n0;
+        st.a[j] = n1;
+    }
+}
+
+template <int Q, int NL>
+__device__ __forceinline__ void bwd_group(PackedState<NL>& ps, PackedState<NL>& lm, float ar, float ai, float br,
+                                          float bi, int lane, float& mX, float& mY, float& mZ) {
+    constexpr int NA = 1 << NL;
+    constexpr int bit = 1 << Q;
+    // yx = (m_Y, m_X) accumulated as one packed value (two chains), z = m_Z scalar (two chains)
+    u64 yx0 = 0ull, yx1 = 0ull;
+    float z0 = 0.f, z1 = 0.f;
+    int t = 0;
+#pragma unroll
+    for (int i = 0; i < NA; ++i) {
+        if (i & bit) continue;
+        const int j = i | bit;
+        const u64 p0 = ps.a[i], p1 = ps.a[j];
+        float l0r, l0i, l1r, l1i, p0r, p0i, p1r, p1i;
+        unpack2(lm.a[i], l0r, l0i);
+        unpack2(lm.a[j], l1r, l1i);
+        unpack2(p0, p0r, p0i);
+        unpack2(p1, p1r, p1i);
+        u64 yx = (t & 1) ? yx1 : yx0;
+        float z = (t & 1) ? z1 : z0;
+        // (m_Y, m_X) += (-Re, Im) of conj(l0) p1  +  (Re, Im) of conj(l1) p0
+        yx = fma2<4>(l0r, p1, yx);     // l0r * (-p1r,  p1i)
+        yx = fma2<7>(l0i, p1, yx);     // l0i * (-p1i, -p1r)
+        yx = fma2<0>(l1r, p0, yx);     // l1r * ( p0r,  p0i)
+        yx = fma2<3>(l1i, p0, yx);     // l1i * ( p0i, -p0r)
+        // m_Z += Im(conj(l0) p0) - Im(conj(l1) p1)
+        z = fmaf(l0r, p0i, z); z = fmaf(-l0i, p0r, z);
+        z = fmaf(-l1r, p1i, z); z = fmaf(l1i, p1r, z);
+        if (t & 1) { yx1 = yx; z1 = z; } else { yx0 = yx; z0 = z; }
+        ++t;
+    }
+    mY = lo2(yx0) + lo2(yx1);
+    mX = hi2(yx0) + hi2(yx1);
+    mZ = z0 + z1;
+    apply_u<Q, true>(ps, ar, ai, br, bi, lane);
+    apply_u<Q, true>(lm, ar, ai, br, bi, lane);
+}
+
+template <int C, int TG, int NL>
+__device__ __forceinline__ void cnot(PackedState<NL>& st, int) {
+#pragma unroll
+    for (int i = 0; i < (1 << NL); ++i) {
+        if (((i >> C) & 1) && !((i >> TG) & 1)) {
+            const int j = i | (1 << TG);
+            const u64 t = st.a[i]; st.a[i] = st.a[j]; st.a[j] = t;
+        }
+    }
+}
+
+template <int NL>
+__device__ __forceinline__ void init_zero_state(PackedState<NL>& st, bool owner) {
+#pragma unroll
+    for (int i = 0; i < (1 << NL); ++i) st.a[i] = 0ull;
+    st.a[0] = pack2(owner ? 1.f : 0.f, 0.f);
+}
+
+template <int NL>
+__device__ __forceinline__ void scale_state(PackedState<NL>& st, float g) {
+#pragma unroll
+    for (int i = 0; i < (1 << NL); ++i) st.a[i] = mul2<0>(g, st.a[i]);
+}
+
+template <int NL>
+__device__ __forceinline__ float real_dot(const PackedState<NL>& a, const PackedState<NL>& b) {
+    u64 e0 = 0ull, e1 = 0ull;
+#pragma unroll
+    for (int i = 0; i < (1 << NL); ++i) {
+        if (i & 1) e1 = fma2_vv(a.a[i], b.a[i], e1);
+        else e0 = fma2_vv(a.a[i], b.a[i], e0);
+    }
+    return (lo2(e0) + hi2(e0)) + (lo2(e1) + hi2(e1));
+}
+
+template <int LQ, int NL>
+__device__ __forceinline__ void apply_ham(const HeaParams<float>& p, const PackedState<NL>& ps, PackedState<NL>& lm,
+                                          int) {
+    static_assert(LQ == 0, "packed state is single-lane");
+    constexpr int NA = 1 << NL;
+    if (p.pauli == 0) {
+#pragma unroll
+        for (int i = 0; i < NA; ++i) lm.a[i] = mul2<0>(__ldg(p.hdiag + i), ps.a[i]);
+        return;
+    }
+    const bool isY = p.pauli == 2;
+#pragma unroll
+    for (int i = 0; i < NA; ++i) lm.a[i] = mul2<0>(p.offset, ps.a[i]);
+    static_for<NL>([&](auto Qc) {
+        constexpr int Q = decltype(Qc)::value;
+#pragma unroll
+        for (int i = 0; i < NA; ++i) {
+            const u64 f = ps.a[i ^ (1 << Q)];
+            if (!isY) {
+                lm.a[i] = fma2<0>(p.coeff, f, lm.a[i]);
+            } else {
+                const float sg = ((i >> Q) & 1) ? p.coeff : -p.coeff;   // +i f if bit set else -i f
+                lm.a[i] = fma2<2>(sg, f, lm.a[i]);
+            }
+        }
+    });
+}
+
+// =================================================================================================
+// shared pieces
+// =================================================================================================
+template <int LQ, bool REVERSE, typename State>
+__device__ __forceinline__ void cnot_ring(State& st, int lane) {
+    constexpr int NQ = State::NL + LQ;
+    if constexpr (NQ > 1) {
+        static_for<NQ>([&](auto I) {
+            constexpr int i = REVERSE ? (NQ - 1 - decltype(I)::value) : decltype(I)::value;
+            cnot<(i + 1) % NQ, i>(st, lane);
+        });
+    }
 }
 
 // sum v[0..VP) over the 32 lanes; afterwards lane l with (l & (32/VP - 1)) == 0 holds slot l / (32/VP)
@@ -253,12 +445,29 @@ __device__ __forceinline__ T butterfly_reduce(T (&v)[VP], int lane) {
     return v[0];
 }
 
+template <typename T>
+__device__ __forceinline__ void fold_rx_coef(const Vec4<T>& u, T theta, T& ar, T& ai, T& br, T& bi) {
+    T sn, cs;
+    sincos_half(theta, sn, cs);
+    ar = fma_(sn, u.w, u.x * cs); ai = fma_(sn, u.z, u.y * cs);
+    br = fma_(-sn, u.y, u.z * cs); bi = fma_(-sn, u.x, u.w * cs);
+}
+
+template <typename T, int NL, int LQ>
+struct StateOf {
+    using type = ScalarState<T, NL>;
+};
+template <int NL>
+struct StateOf<float, NL, 0> {
+    using type = PackedState<NL>;
+};
+
 // ------------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------------
 template <typename T, int NL, int LQ, bool GRAD, bool NEED_GX, int THREADS, int MIN_BLOCKS>
 __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) hea_reg_kernel(const HeaParams<T> p) {
-    constexpr int NA = 1 << NL;
+    using State = typename StateOf<T, NL, LQ>::type;
     constexpr int NQ = NL + LQ;
     constexpr int SPW = 32 >> LQ;                 // samples per warp
     constexpr int VP = moment_slots(NQ);
@@ -279,10 +488,8 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) hea_reg_kernel(const HeaP
         const bool valid = b < p.B;
         const T* xrow = p.x + (valid ? b : p.B - 1) * p.ldx;
 
-        T pr[NA], pi[NA];
-#pragma unroll
-        for (int i = 0; i < NA; ++i) { pr[i] = 0; pi[i] = 0; }
-        pr[0] = sub == 0 ? T(1) : T(0);
+        State ps;
+        init_zero_state(ps, sub == 0);
 
         // ---------------- forward sweep ----------------
         {
@@ -296,29 +503,17 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) hea_reg_kernel(const HeaP
 #pragma unroll
                 for (int q = 0; q < NQ; ++q) thn[q] = __ldg(xrow + (int64_t)kn * NQ + q);   // prefetch next block
                 const int d = __ldg(p.depth + k);
-                {   // first sublayer, RX folded in
+#pragma unroll 1
+                for (int j = 0; j < d; ++j, ++s) {
                     const Vec4<T>* uc = p.ucoef + (int64_t)s * NQ;
                     static_for<NQ>([&](auto Qc) {
                         constexpr int Q = decltype(Qc)::value;
                         const Vec4<T> u = ldg4(uc + Q);
-                        T sn, cs;
-                        sincos_half(th[Q], sn, cs);
-                        const T ar = fma_(sn, u.w, u.x * cs), ai = fma_(sn, u.z, u.y * cs);
-                        const T br = fma_(-sn, u.y, u.z * cs), bi = fma_(-sn, u.x, u.w * cs);
-                        apply_u<T, NL, Q, false>(pr, pi, ar, ai, br, bi, lane);
+                        T ar = u.x, ai = u.y, br = u.z, bi = u.w;
+                        if (j == 0) fold_rx_coef(u, th[Q], ar, ai, br, bi);   // first sublayer: RX folded in
+                        apply_u<Q, false>(ps, ar, ai, br, bi, lane);
                     });
-                    cnot_ring<T, NL, LQ, false>(pr, pi, lane);
-                    ++s;
-                }
-                for (int j = 1; j < d; ++j) {
-                    const Vec4<T>* uc = p.ucoef + (int64_t)s * NQ;
-                    static_for<NQ>([&](auto Qc) {
-                        constexpr int Q = decltype(Qc)::value;
-                        const Vec4<T> u = ldg4(uc + Q);
-                        apply_u<T, NL, Q, false>(pr, pi, u.x, u.y, u.z, u.w, lane);
-                    });
-                    cnot_ring<T, NL, LQ, false>(pr, pi, lane);
-                    ++s;
+                    cnot_ring<LQ, false>(ps, lane);
                 }
 #pragma unroll
                 for (int q = 0; q < NQ; ++q) th[q] = thn[q];
@@ -326,20 +521,25 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) hea_reg_kernel(const HeaP
         }
 
         // ---------------- expectation value ----------------
-        T lr[NA], li[NA];
-        apply_ham<T, NL, LQ>(p, pr, pi, lr, li, lane);
-        T e = 0;
-#pragma unroll
-        for (int i = 0; i < NA; ++i) { e = fma_(pr[i], lr[i], e); e = fma_(pi[i], li[i], e); }
+        State lm;
+        apply_ham<LQ>(p, ps, lm, lane);
+        T e = real_dot(ps, lm);
 #pragma unroll
         for (int m = 1; m < (1 << LQ); m <<= 1) e += shfl_xor_(e, m);
         if (valid && sub == 0) p.out[b] = e;
 
         if constexpr (GRAD) {
             // ---------------- reverse (adjoint) sweep ----------------
-            const T g = valid ? __ldg(p.gout + b) : T(0);
-#pragma unroll
-            for (int i = 0; i < NA; ++i) { lr[i] *= g; li[i] *= g; }
+            T g = T(0);
+            if (valid) {
+                if (p.target) {   // fused MSE: g = dL/dout for L = gscale/2 * sum (out + bias - y)^2
+                    g = p.gscale * (e + (p.bias ? __ldg(p.bias) : T(0)) - __ldg(p.target + b));
+                    if (sub == 0) p.gbuf[b] = g;
+                } else {
+                    g = __ldg(p.gout + b);
+                }
+            }
+            scale_state(lm, g);
             T* gxrow = NEED_GX ? p.gx + (valid ? b : 0) * p.ldgx : nullptr;
             int s = p.S;
             T th[NQ];
@@ -351,48 +551,33 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) hea_reg_kernel(const HeaP
 #pragma unroll
                 for (int q = 0; q < NQ; ++q) thn[q] = __ldg(xrow + (int64_t)kn * NQ + q);
                 const int d = __ldg(p.depth + k);
-                for (int j = d - 1; j >= 1; --j) {
-                    --s;
-                    const Vec4<T>* uc = p.ucoef + (int64_t)s * NQ;
-                    cnot_ring<T, NL, LQ, true>(pr, pi, lane);
-                    cnot_ring<T, NL, LQ, true>(lr, li, lane);
-                    T mv[VP];
-#pragma unroll
-                    for (int i = 0; i < VP; ++i) mv[i] = 0;
-                    static_for<NQ>([&](auto Qc) {
-                        constexpr int Q = NQ - 1 - decltype(Qc)::value;
-                        const Vec4<T> u = ldg4(uc + Q);
-                        bwd_group<T, NL, Q>(pr, pi, lr, li, u.x, u.y, u.z, u.w, lane, mv[3 * Q], mv[3 * Q + 1], mv[3 * Q + 2]);
-                    });
-                    const T tot = butterfly_reduce<T, VP>(mv, lane);
-                    if ((lane & (32 / VP - 1)) == 0) atomicAdd(mrow + (int64_t)s * VP + lane / (32 / VP), tot);
-                }
-                {   // first sublayer of the block (RX folded in): also yields dL/dx
+#pragma unroll 1
+                for (int j = d - 1; j >= 0; --j) {
                     --s;
                     const Vec4<T>* uc = p.ucoef + (int64_t)s * NQ;
                     const Vec4<T>* rc = p.rcoef + (int64_t)s * NQ;
-                    cnot_ring<T, NL, LQ, true>(pr, pi, lane);
-                    cnot_ring<T, NL, LQ, true>(lr, li, lane);
+                    cnot_ring<LQ, true>(ps, lane);
+                    cnot_ring<LQ, true>(lm, lane);
                     T mv[VP];
 #pragma unroll
                     for (int i = 0; i < VP; ++i) mv[i] = 0;
                     static_for<NQ>([&](auto Qc) {
                         constexpr int Q = NQ - 1 - decltype(Qc)::value;
                         const Vec4<T> u = ldg4(uc + Q);
-                        T sn, cs;
-                        sincos_half(th[Q], sn, cs);
-                        const T ar = fma_(sn, u.w, u.x * cs), ai = fma_(sn, u.z, u.y * cs);
-                        const T br = fma_(-sn, u.y, u.z * cs), bi = fma_(-sn, u.x, u.w * cs);
-                        bwd_group<T, NL, Q>(pr, pi, lr, li, ar, ai, br, bi, lane, mv[3 * Q], mv[3 * Q + 1], mv[3 * Q + 2]);
+                        T ar = u.x, ai = u.y, br = u.z, bi = u.w;
+                        if (j == 0) fold_rx_coef(u, th[Q], ar, ai, br, bi);
+                        bwd_group<Q>(ps, lm, ar, ai, br, bi, lane, mv[3 * Q], mv[3 * Q + 1], mv[3 * Q + 2]);
                         if constexpr (NEED_GX) {
-                            T mx = mv[3 * Q], my = mv[3 * Q + 1], mz = mv[3 * Q + 2];
+                            if (j == 0) {   // dL/dx of the folded RX from the three moments
+                                T mx = mv[3 * Q], my = mv[3 * Q + 1], mz = mv[3 * Q + 2];
 #pragma unroll
-                            for (int m = 1; m < (1 << LQ); m <<= 1) {
-                                mx += shfl_xor_(mx, m); my += shfl_xor_(my, m); mz += shfl_xor_(mz, m);
+                                for (int m = 1; m < (1 << LQ); m <<= 1) {
+                                    mx += shfl_xor_(mx, m); my += shfl_xor_(my, m); mz += shfl_xor_(mz, m);
+                                }
+                                const Vec4<T> r = ldg4(rc + Q);
+                                const T gxv = fma_(r.z, mz, fma_(r.y, my, r.x * mx));
+                                if (valid && sub == 0) gxrow[(int64_t)k * NQ + Q] = gxv;
                             }
-                            const Vec4<T> r = ldg4(rc + Q);
-                            const T gxv = fma_(r.z, mz, fma_(r.y, my, r.x * mx));
-                            if (valid && sub == 0) gxrow[(int64_t)k * NQ + Q] = gxv;
                         }
                     });
                     const T tot = butterfly_reduce<T, VP>(mv, lane);

@@ -254,14 +254,17 @@ int make_plan(int64_t B, int n, int K, const int* depth, int dtype, int mode, Pl
 }
 
 template <typename T>
-int run(const void* x, int64_t ldx, const void* w, const void* grad_out, void* out, void* grad_x, int64_t ldgx,
+int run(const void* x, int64_t ldx, const void* w, const void* grad_out, const void* target, const void* bias,
+        double gscale, void* gbuf, void* out, void* grad_x, int64_t ldgx,
         void* grad_w, int64_t B, int n, int K, const int* depth, const void* ham_diag, int diag_order,
         double offset, double coeff, int ham_kind, int dtype, void* ws, size_t ws_bytes, void* stream, bool grad) {
     const int mode = !grad ? 0 : (grad_x ? 1 : 2);
     Plan pl;
     if (int rc = make_plan(B, n, K, depth, dtype, mode, &pl)) return rc;
     if (!x || !w || !out) return fail(QON_ERR_BAD_ARG, "x, w and out must be non-NULL");
-    if (grad && (!grad_out || !grad_w)) return fail(QON_ERR_BAD_ARG, "grad_out and grad_w must be non-NULL");
+    if (grad && !grad_w) return fail(QON_ERR_BAD_ARG, "grad_w must be non-NULL");
+    if (grad && !grad_out && !target) return fail(QON_ERR_BAD_ARG, "grad_out (or target) must be non-NULL");
+    if (target && !gbuf) return fail(QON_ERR_BAD_ARG, "grad_out_written must be non-NULL when target is given");
     if (ldx < (int64_t)n * K) return fail(QON_ERR_BAD_ARG, "ldx (%lld) < n*K (%d)", (long long)ldx, n * K);
     if (grad_x && ldgx < (int64_t)n * K) return fail(QON_ERR_BAD_ARG, "ldgx (%lld) < n*K (%d)", (long long)ldgx, n * K);
     if (ham_kind < QON_HAM_DIAG || ham_kind > QON_HAM_PAULI_Y) return fail(QON_ERR_BAD_ARG, "bad ham_kind %d", ham_kind);
@@ -278,6 +281,7 @@ int run(const void* x, int64_t ldx, const void* w, const void* grad_out, void* o
     HeaParams<T> p{};
     p.x = (const T*)x; p.ldx = ldx; p.B = B; p.out = (T*)out;
     p.gout = (const T*)grad_out; p.gx = (T*)grad_x; p.ldgx = ldgx;
+    p.target = (const T*)target; p.bias = (const T*)bias; p.gbuf = (T*)gbuf; p.gscale = (T)gscale;
     p.ucoef = (const Vec4<T>*)(base + pl.off_u);
     p.rcoef = (const Vec4<T>*)(base + pl.off_r);
     p.hdiag = (const T*)(base + pl.off_h);
@@ -339,9 +343,14 @@ const char* qon_last_error(void) { return g_err.c_str(); }
 
 size_t qon_workspace_bytes(int64_t B, int n, int K, const int* depth_per_block, int dtype, int need_grad) {
     Plan pl;
-    // mode 1 and 2 need the same workspace
     if (make_plan(B, n, K, depth_per_block, dtype, need_grad ? 1 : 0, &pl)) return 0;
-    return pl.total;
+    size_t total = pl.total;
+    if (need_grad) {   // with / without dL/dx are different kernels (different occupancy -> different row count)
+        Plan pl2;
+        if (make_plan(B, n, K, depth_per_block, dtype, 2, &pl2)) return 0;
+        if (pl2.total > total) total = pl2.total;
+    }
+    return total;
 }
 
 int qon_plan_tier(int64_t B, int n, int dtype, int need_grad, int* lanes_log2) {
@@ -356,10 +365,10 @@ int qon_hea_forward(const void* x, int64_t ldx, const void* w, void* out, int64_
                     const int* depth_per_block, const void* ham_diag, int diag_order, double ham_offset,
                     double ham_coeff, int ham_kind, int dtype, void* workspace, size_t workspace_bytes, void* stream) {
     if (dtype == QON_F32)
-        return run<float>(x, ldx, w, nullptr, out, nullptr, 0, nullptr, B, n, K, depth_per_block, ham_diag, diag_order,
+        return run<float>(x, ldx, w, nullptr, nullptr, nullptr, 0.0, nullptr, out, nullptr, 0, nullptr, B, n, K, depth_per_block, ham_diag, diag_order,
                           ham_offset, ham_coeff, ham_kind, dtype, workspace, workspace_bytes, stream, false);
     if (dtype == QON_F64)
-        return run<double>(x, ldx, w, nullptr, out, nullptr, 0, nullptr, B, n, K, depth_per_block, ham_diag, diag_order,
+        return run<double>(x, ldx, w, nullptr, nullptr, nullptr, 0.0, nullptr, out, nullptr, 0, nullptr, B, n, K, depth_per_block, ham_diag, diag_order,
                            ham_offset, ham_coeff, ham_kind, dtype, workspace, workspace_bytes, stream, false);
     return fail(QON_ERR_BAD_ARG, "dtype must be QON_F32 or QON_F64");
 }
@@ -369,11 +378,28 @@ int qon_hea_forward_backward(const void* x, int64_t ldx, const void* w, const vo
                              const void* ham_diag, int diag_order, double ham_offset, double ham_coeff, int ham_kind,
                              int dtype, void* workspace, size_t workspace_bytes, void* stream) {
     if (dtype == QON_F32)
-        return run<float>(x, ldx, w, grad_out, out, grad_x, ldgx, grad_w, B, n, K, depth_per_block, ham_diag, diag_order,
+        return run<float>(x, ldx, w, grad_out, nullptr, nullptr, 0.0, nullptr, out, grad_x, ldgx, grad_w, B, n, K, depth_per_block, ham_diag, diag_order,
                           ham_offset, ham_coeff, ham_kind, dtype, workspace, workspace_bytes, stream, true);
     if (dtype == QON_F64)
-        return run<double>(x, ldx, w, grad_out, out, grad_x, ldgx, grad_w, B, n, K, depth_per_block, ham_diag, diag_order,
+        return run<double>(x, ldx, w, grad_out, nullptr, nullptr, 0.0, nullptr, out, grad_x, ldgx, grad_w, B, n, K, depth_per_block, ham_diag, diag_order,
                            ham_offset, ham_coeff, ham_kind, dtype, workspace, workspace_bytes, stream, true);
+    return fail(QON_ERR_BAD_ARG, "dtype must be QON_F32 or QON_F64");
+}
+
+int qon_hea_mse_forward_backward(const void* x, int64_t ldx, const void* w, const void* target, const void* bias,
+                                 double grad_scale, void* out, void* grad_out_written, void* grad_x, int64_t ldgx,
+                                 void* grad_w, int64_t B, int n, int K, const int* depth_per_block,
+                                 const void* ham_diag, int diag_order, double ham_offset, double ham_coeff, int ham_kind,
+                                 int dtype, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!target) return fail(QON_ERR_BAD_ARG, "target must be non-NULL");
+    if (dtype == QON_F32)
+        return run<float>(x, ldx, w, nullptr, target, bias, grad_scale, grad_out_written, out, grad_x, ldgx, grad_w, B, n,
+                          K, depth_per_block, ham_diag, diag_order, ham_offset, ham_coeff, ham_kind, dtype, workspace,
+                          workspace_bytes, stream, true);
+    if (dtype == QON_F64)
+        return run<double>(x, ldx, w, nullptr, target, bias, grad_scale, grad_out_written, out, grad_x, ldgx, grad_w, B,
+                           n, K, depth_per_block, ham_diag, diag_order, ham_offset, ham_coeff, ham_kind, dtype, workspace,
+                           workspace_bytes, stream, true);
     return fail(QON_ERR_BAD_ARG, "dtype must be QON_F32 or QON_F64");
 }
 

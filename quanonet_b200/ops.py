@@ -162,3 +162,49 @@ def plan_tier(B: int, n: int, dtype=torch.float32, need_grad=True):
     if t < 0:
         raise RuntimeError(_lib.last_error())
     return t, lq.value
+
+
+@torch.library.custom_op("quanonet::hea_mse_backward", mutates_args=())
+def hea_mse_backward(x: torch.Tensor, weights: torch.Tensor, target: torch.Tensor, bias: Optional[torch.Tensor],
+                     grad_scale: float, n_wires: int, depth_per_block: List[int], ham_diag: Optional[torch.Tensor],
+                     diag_order: int, ham_offset: float, ham_coeff: float, ham_kind: int,
+                     need_grad_x: bool) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
+    """Training-step kernel: forward, MSE upstream gradient ``g = grad_scale*(out+bias-target)`` and
+    adjoint backward in ONE pass (``qon_hea_mse_forward_backward``).
+    Returns (out (B,1) without bias, g (B,), grad_x (B,n*K) or empty, grad_w (S,3,n))."""
+    _check_inputs(x, weights, n_wires, depth_per_block, ham_diag)
+    lib = _lib.load()
+    code = _DTYPES[x.dtype]
+    B = x.shape[0]
+    out = torch.empty((B, 1), dtype=x.dtype, device=x.device)
+    g = torch.empty((B,), dtype=x.dtype, device=x.device)
+    grad_w = torch.empty_like(weights, memory_format=torch.contiguous_format)
+    grad_x = torch.empty((B, x.shape[1]) if need_grad_x else (0,), dtype=x.dtype, device=x.device)
+    with torch.cuda.device(x.device):
+        xc, ldx = _rowmajor(x)
+        wc = weights.contiguous()
+        y = target.to(dtype=x.dtype).reshape(-1).contiguous()
+        if y.numel() != B:
+            raise ValueError(f"target must have B = {B} elements, got {y.numel()}")
+        bptr = None
+        if bias is not None:
+            bc = bias.to(dtype=x.dtype).reshape(-1).contiguous()
+            bptr = bc.data_ptr()
+        hd = None if ham_diag is None else ham_diag.to(dtype=x.dtype, device=x.device).contiguous()
+        depth = _lib.int_array(depth_per_block)
+        ws, nbytes = _workspace(B, n_wires, depth, code, True, x.device)
+        stream = torch.cuda.current_stream(x.device).cuda_stream
+        rc = lib.qon_hea_mse_forward_backward(
+            xc.data_ptr(), ldx, wc.data_ptr(), y.data_ptr(), bptr, float(grad_scale), out.data_ptr(), g.data_ptr(),
+            grad_x.data_ptr() if need_grad_x else None, max(int(x.shape[1]), 1), grad_w.data_ptr(),
+            B, n_wires, len(depth_per_block), depth, None if hd is None else hd.data_ptr(), diag_order,
+            ham_offset, ham_coeff, ham_kind, code, ws.data_ptr(), nbytes, stream)
+        _lib.check(rc, "qon_hea_mse_forward_backward")
+    return out, g, grad_x, grad_w
+
+
+@hea_mse_backward.register_fake
+def _(x, weights, target, bias, grad_scale, n_wires, depth_per_block, ham_diag, diag_order, ham_offset, ham_coeff,
+      ham_kind, need_grad_x):
+    gx = x.new_empty(x.shape if need_grad_x else (0,))
+    return x.new_empty((x.shape[0], 1)), x.new_empty((x.shape[0],)), gx, torch.empty_like(weights)
