@@ -198,7 +198,7 @@ def run_b200(args):
     import torch.distributed as dist
     from quanonet_b200 import _lib
     from quanonet_b200.ops import fp32_peak_tflops, hea_expval
-    from quanonet_b200.train import DataParallelTrainer, _default_kernel
+    from quanonet_b200.train import DataParallelTrainer
 
     _lib.load()                                   # fail loudly if the CUDA library is missing
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -215,17 +215,8 @@ def run_b200(args):
     f_fwd, f_all = alg_flops()
 
     model = make_model(dev, seed=0)
-    kernel_events = []
-
-    def timed_kernel(*a):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        r = _default_kernel(*a)
-        e1.record()
-        kernel_events.append((e0, e1))
-        return r
-
-    trainer = DataParallelTrainer(model, lr=1e-3, optimizer="adam", kernel_fn=timed_kernel)
+    trainer = DataParallelTrainer(model, lr=1e-3, optimizer="adam", use_fused_encoding=not args.unfused)
+    kernel_events = trainer.kernel_events = []
     branch, trunk, y = synth_batch(B, seed=100 + rank, device=dev)
     peak = fp32_peak_tflops(4000) if rank == 0 else None
 
@@ -337,9 +328,10 @@ def run_b200(args):
         nominal = 148 * 128 * 2 * 1.965e9 / 1e12
         traffic = None
         tf = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(tf):
+        if os.path.exists(tf):   # dram bytes per SAMPLE from the committed `ncu --set full` capture
             try:
-                traffic = json.load(open(tf)).get("hea_reg_kernel_fwd_grad_bytes_per_launch")
+                key = "fused_encoding_bytes_per_sample" if trainer.fused_encoding else "x_given_bytes_per_sample"
+                traffic = json.load(open(tf))[key] * B
             except Exception:
                 traffic = None
         line = {
@@ -349,14 +341,18 @@ def run_b200(args):
             "config": {"workload": WORKLOAD, "num_qubits": N_QUBITS, "net_size": list(NET),
                        "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world}",
                        "l2_policy": "inputs larger than L2: per-step inputs 412 MB + 1.2 GB encoding matrix vs 126 MB L2",
-                       "step": "freq layers + fused fwd/MSE/adjoint-grad kernel + chain rule + all-reduce + Adam"},
+                       "step": ("ONE kernel: frequency layers + forward + MSE + adjoint-grad + batch reduction of all "
+                                "2,401 gradients; then all-reduce + Adam" if trainer.fused_encoding else
+                                "freq layers (torch) + fused fwd/MSE/adjoint-grad kernel + chain rule (torch) + "
+                                "all-reduce + Adam")},
             "clocks": sampler.summary(),
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "ms_per_step": e2e_ms / K},
-            "gpu_launches": 3 * K,
+            "gpu_launches": (4 if trainer.fused_encoding else 3) * K,
             "roofline": {"bound": "fp32", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                          "frac": achieved / peak if peak else None, "traffic": traffic,
-                         "kernel": "hea_reg_kernel<float,5,0,grad> (+prep, finalize)", "kernel_ms": kern_ms,
+                         "kernel": "hea_reg_kernel<float,5,0,grad%s> (+prep, finalize)" % (
+                             ",fused-encoding" if trainer.fused_encoding else ""), "kernel_ms": kern_ms,
                          "flops_per_sample": f_all, "peak_source": "FFMA probe measured on this GPU in this run "
                          "(MEASURED_PEAKS.json has no FP32 entry)", "peak_nominal": nominal,
                          "frac_of_nominal": achieved / nominal},
@@ -380,6 +376,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=1_000_000, help="samples per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--unfused", action="store_true",
+                    help="materialise the encoding matrix with torch ops instead of the fused-encoding kernel")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

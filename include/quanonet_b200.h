@@ -108,6 +108,36 @@ int qon_hea_mse_forward_backward(const void* x, int64_t ldx, const void* w, cons
                                  const void* ham_diag, int diag_order, double ham_offset, double ham_coeff,
                                  int ham_kind, int dtype, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- Fused encoding ("the model in one kernel") ------------------------------------------------------
+ * The callers of the circuit, QuanONetPT.forward / HEAQNNPT.forward (core/models_pt.py:153-166,205-213),
+ * build the encoding-angle matrix x = cat([trunk_enc, branch_enc]) with the frequency layers
+ * _TiledElementWise / _ScaleRepeat (core/models_pt.py:14-68):  x[b,c] = fw[c] * u_src(c)[b, local(c) % in] + fb[c],
+ * src(c) = source 0 (trunk) for the first K0 blocks, source 1 (branch) afterwards; local(c) = column index
+ * within its source.  These entry points evaluate that inside the kernel, so x and grad_x (1.2 KB per sample
+ * each at Q5 Net40-2-20-2) are never materialised.  Register tier only (n <= 5 fp32, n <= 4 fp64).
+ *   u0  device (B, in0) row stride ldu0 — may be NULL when K0 == 0 (HEAQNN);   u1  device (B, in1), stride ldu1
+ *   fw  device (n*K,) frequency weights (fixed-scale mode: the constant scale);  fb  device (n*K,) or NULL
+ */
+int qon_encoded_forward(const void* u0, int64_t ldu0, int in0, int K0, const void* u1, int64_t ldu1, int in1,
+                        const void* fw, const void* fb, const void* w, void* out, int64_t B, int n, int K,
+                        const int* depth_per_block, const void* ham_diag, int diag_order, double ham_offset,
+                        double ham_coeff, int ham_kind, int dtype, void* workspace, size_t workspace_bytes,
+                        void* stream);
+
+/* One training step's gradient in one pass: frequency layers, forward, MSE upstream gradient
+ * g[b] = grad_scale*(out[b] + bias - target[b]), adjoint backward, and the batch reductions of ALL parameter
+ * gradients (replaces solvers/solver_pt.py:231-235 for QuanONetPT / HEAQNNPT).
+ *   out      device (B,) or NULL       expectation values without bias
+ *   grad_w   device (S,3,n)            overwritten
+ *   grad_fw, grad_fb  device (n*K,) or both NULL (fixed-scale encoders)   overwritten
+ *   sums     device (2,)               [sum_b g[b] (= dL/dbias),  sum_b (out+bias-target)^2] */
+int qon_encoded_mse_step(const void* u0, int64_t ldu0, int in0, int K0, const void* u1, int64_t ldu1, int in1,
+                         const void* fw, const void* fb, const void* w, const void* target, const void* bias,
+                         double grad_scale, void* out, void* grad_w, void* grad_fw, void* grad_fb, void* sums,
+                         int64_t B, int n, int K, const int* depth_per_block, const void* ham_diag, int diag_order,
+                         double ham_offset, double ham_coeff, int ham_kind, int dtype, void* workspace,
+                         size_t workspace_bytes, void* stream);
+
 /* Which kernel tier a problem maps to on the current device: 0 = register tier (state in registers,
  * 2^lanes_log2 lanes per sample), 1 = shared-memory tier, 2 = HBM-streamed tier; -1 = unsupported. */
 int qon_plan_tier(int64_t B, int n, int dtype, int need_grad, int* lanes_log2);

@@ -10,7 +10,8 @@ import os
 import threading
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG_DIR, "libquanonet_b200.so")
+# QON_LIB_PATH selects an experiment build of the same library (scripts/build_variant.sh); never a fallback
+LIB_PATH = os.environ.get("QON_LIB_PATH") or os.path.join(PKG_DIR, "libquanonet_b200.so")
 
 QON_F32, QON_F64 = 0, 1
 QON_HAM_DIAG, QON_HAM_PAULI_X, QON_HAM_PAULI_Y = 0, 1, 2
@@ -25,6 +26,8 @@ EXPORTED_SYMBOLS = (
     "qon_hea_forward",
     "qon_hea_forward_backward",
     "qon_hea_mse_forward_backward",
+    "qon_encoded_forward",
+    "qon_encoded_mse_step",
     "qon_plan_tier",
     "qon_measure_fp32_peak_tflops",
 )
@@ -55,6 +58,12 @@ def _declare(lib):
     lib.qon_hea_mse_forward_backward.restype = i32
     lib.qon_hea_mse_forward_backward.argtypes = [vp, i64, vp, vp, vp, dbl, vp, vp, vp, i64, vp, i64, i32, i32, ip,
                                                  vp, i32, dbl, dbl, i32, i32, vp, sz, vp]
+    ham_tail = [vp, i32, dbl, dbl, i32, i32, vp, sz, vp]   # ham_diag, diag_order, offset, coeff, kind, dtype, ws, bytes, stream
+    enc_head = [vp, i64, i32, i32, vp, i64, i32, vp, vp]   # u0, ldu0, in0, K0, u1, ldu1, in1, fw, fb
+    lib.qon_encoded_forward.restype = i32
+    lib.qon_encoded_forward.argtypes = enc_head + [vp, vp, i64, i32, i32, ip] + ham_tail
+    lib.qon_encoded_mse_step.restype = i32
+    lib.qon_encoded_mse_step.argtypes = enc_head + [vp, vp, vp, dbl, vp, vp, vp, vp, vp, i64, i32, i32, ip] + ham_tail
     lib.qon_plan_tier.restype = i32
     lib.qon_plan_tier.argtypes = [i64, i32, i32, i32, ip]
     lib.qon_measure_fp32_peak_tflops.restype = dbl

@@ -66,6 +66,39 @@ def _build_quantum_layer(quantum_backend, num_qubits, total_input_size, net_size
     return build_heaqnn_tq(num_qubits, total_input_size, net_size, ham_bound=ham_bound, ham_diag=ham_diag, **extra)
 
 
+def _can_fuse_inference(qlayer, u):
+    """Inference (no autograd) on CUDA in the register tier: evaluate the frequency layers inside the
+    kernel (``quanonet::encoded_expval``) instead of materialising the encoding matrix."""
+    if torch.is_grad_enabled() or not u.is_cuda:
+        return False
+    from ..ops import encoded_supported
+    w = qlayer.ansatz_weights
+    return (encoded_supported(qlayer.n_wires, w.dtype)
+            and all(e == qlayer.n_wires and d >= 1 for e, d in qlayer.block_configs))
+
+
+def _fused_inference(qlayer, layers, u0, u1, enc0):
+    from .. import _lib
+    from ..ops import encoded_expval
+    from .quantum_circuits_tq import _DIAG_ORDER, _PAULI_KIND
+    w = qlayer.ansatz_weights
+    if isinstance(layers[0], _TiledElementWise):
+        fw = torch.cat([l.weights for l in layers])
+        fb = torch.cat([l.bias for l in layers])
+    else:
+        fw = torch.cat([torch.full((l.out_features,), float(l.scale), dtype=w.dtype, device=w.device) for l in layers])
+        fb = None
+    depths = [d for _, d in qlayer.block_configs]
+    u1 = u1.to(w.dtype)
+    u0 = None if u0 is None else u0.to(w.dtype)
+    if qlayer.use_full_ham:
+        ham = (qlayer.ham_diag.to(device=w.device, dtype=w.dtype), _DIAG_ORDER[qlayer.diag_order], 0.0, 0.0,
+               _lib.QON_HAM_DIAG)
+    else:
+        ham = (None, _lib.QON_DIAG_LSB0, qlayer.ham_offset, qlayer.ham_coeff, _PAULI_KIND[qlayer.ham_pauli])
+    return encoded_expval(u0, u1, fw, fb, enc0 // qlayer.n_wires, w, qlayer.n_wires, depths, *ham)
+
+
 class QuanONetPT(nn.Module):
     """``forward(branch_input (B, b_in), trunk_input (B, t_in)) -> (B,1)``:
     frequency layers -> ``cat([trunk_enc, branch_enc])`` -> quantum layer -> ``+ bias``
@@ -88,6 +121,9 @@ class QuanONetPT(nn.Module):
         self.bias = nn.Parameter(torch.zeros(1))
 
     def forward(self, branch_input, trunk_input):
+        if _can_fuse_inference(self.quantum_layer, branch_input):
+            return _fused_inference(self.quantum_layer, (self.trunk_freq, self.branch_freq),
+                                    trunk_input, branch_input, self.trunk_enc_size) + self.bias
         x = torch.cat([self.trunk_freq(trunk_input), self.branch_freq(branch_input)], dim=1)
         return self.quantum_layer(x) + self.bias
 
@@ -106,4 +142,6 @@ class HEAQNNPT(nn.Module):
                                                   ham_diag, **extra)
 
     def forward(self, x):
+        if _can_fuse_inference(self.quantum_layer, x):
+            return _fused_inference(self.quantum_layer, (self.freq,), None, x, 0)
         return self.quantum_layer(self.freq(x))

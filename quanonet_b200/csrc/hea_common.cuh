@@ -37,12 +37,27 @@ struct HeaParams {
     const Vec4<T>* rcoef;
     const T* hdiag;      // (2^n,) diagonal of H in LSB0 order (pauli == 0)
     const int* depth;    // (K,) device copy of depth_per_block
-    T* mpart;            // (rows, S*VP) per-warp partial sums of Pauli moments [grad only]
+    T* mpart;            // (rows, rowlen) per-warp partial sums [grad only]; row = [S*VP Pauli moments |
+                         //   K*FVP frequency-layer gradient slots | sum g | sum residual^2 | pad]
+    int64_t rowlen;
     int K;
     int S;
     int pauli;           // 0: diagonal table; 1: offset + coeff*sum X_i; 2: offset + coeff*sum Y_i
     T offset, coeff;
+    // Fused encoding ("ENC" kernels): the angle of column c is  fw[c] * u_src(c)[b, uidx[c]] + fb[c]  with
+    // src(c) = 0 for blocks k < K0 and 1 otherwise — the frequency layers of core/models_pt.py:14-68 and the
+    // trunk-first concatenation of :163-164, evaluated in-kernel so x and grad_x are never materialised.
+    const T* u0;         // (B, in0) rows, stride ldu0  (QuanONet: trunk input; HEAQNN: unused, K0 = 0)
+    const T* u1;         // (B, in1) rows, stride ldu1  (QuanONet: branch input; HEAQNN: the input)
+    int64_t ldu0, ldu1;
+    int K0;
+    const int* uidx;     // (n*K,) source-row index of every column (prep kernel: local column % in)
+    const T* fw;         // (n*K,) frequency weights (fixed-scale mode: the constant scale)
+    const T* fb;         // (n*K,) frequency bias, or null
 };
+
+// slots per block for the frequency-layer gradients: (d/dfw, d/dfb) per qubit, padded for the butterfly
+__host__ __device__ constexpr int freq_slots(int n) { return 2 * n <= 2 ? 2 : (2 * n <= 4 ? 4 : (2 * n <= 8 ? 8 : (2 * n <= 16 ? 16 : 32))); }
 
 __host__ __device__ constexpr int next_pow2(int v) {
     int p = 1;

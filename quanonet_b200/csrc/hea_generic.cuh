@@ -118,7 +118,7 @@ __global__ void hea_generic_kernel(const HeaParams<T> p, const int n, const int 
     T* pi = base + N;
     T* lr = GRAD ? base + 2 * N : nullptr;
     T* li = GRAD ? base + 3 * N : nullptr;
-    T* mrow = GRAD ? p.mpart + (int64_t)blockIdx.x * p.S * VP : nullptr;
+    T* mrow = GRAD ? p.mpart + (int64_t)blockIdx.x * p.rowlen : nullptr;
 
     for (int64_t b = blockIdx.x; b < p.B; b += gridDim.x) {
         const T* xrow = p.x + b * p.ldx;

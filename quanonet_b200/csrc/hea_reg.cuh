@@ -464,15 +464,25 @@ struct StateOf<float, NL, 0> {
 
 // ------------------------------------------------------------------------------------------------
 // the kernel
+//   ENC = 0: encoding angles x given;  1: angles formed in-kernel from (u0, u1, fw, fb);
+//   ENC = 2: as 1, and the frequency-layer gradients dL/dfw, dL/dfb are reduced over the batch in-kernel.
 // ------------------------------------------------------------------------------------------------
-template <typename T, int NL, int LQ, bool GRAD, bool NEED_GX, int THREADS, int MIN_BLOCKS>
+template <typename T, int NL, int LQ, bool GRAD, bool NEED_GX, int ENC, int THREADS, int MIN_BLOCKS>
 __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) hea_reg_kernel(const HeaParams<T> p) {
     using State = typename StateOf<T, NL, LQ>::type;
     constexpr int NQ = NL + LQ;
     constexpr int SPW = 32 >> LQ;                 // samples per warp
     constexpr int VP = moment_slots(NQ);
+    constexpr int FVP = freq_slots(NQ);
     constexpr int WARPS = THREADS / 32;
-    static_assert(VP <= 32, "moment butterfly needs 3n <= 32");
+    constexpr bool FREQ_GRAD = GRAD && ENC == 2;
+    constexpr bool WANT_GX = NEED_GX || FREQ_GRAD;
+    static_assert(VP <= 32 && FVP <= 32, "moment butterfly needs 3n <= 32");
+    static_assert(!(NEED_GX && ENC != 0), "grad_x is only materialised when x is");
+#ifndef QON_SYNC_WARPS
+#define QON_SYNC_WARPS 0
+#endif
+    constexpr bool SYNC_WARPS = QON_SYNC_WARPS != 0;
 
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -481,12 +491,34 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) hea_reg_kernel(const HeaP
     const int64_t gwarp = (int64_t)blockIdx.x * WARPS + warp;
     const int64_t nwarps = (int64_t)gridDim.x * WARPS;
     const int64_t ntiles = (p.B + SPW - 1) / SPW;
-    T* mrow = GRAD ? p.mpart + gwarp * (int64_t)p.S * VP : nullptr;
+    T* mrow = GRAD ? p.mpart + gwarp * p.rowlen : nullptr;
+    T* frow = GRAD ? mrow + (int64_t)p.S * VP : nullptr;             // frequency-gradient slots
+    T* srow = GRAD ? frow + (int64_t)p.K * FVP : nullptr;            // [sum g, sum residual^2]
 
-    for (int64_t tile = gwarp; tile < ntiles; tile += nwarps) {
+    // CTA-uniform trip count (tile0 is the CTA's first tile), so an optional per-sublayer barrier is legal.
+    for (int64_t tile0 = (int64_t)blockIdx.x * WARPS; tile0 < ntiles; tile0 += nwarps) {
+        const int64_t tile = tile0 + warp;
         const int64_t b = tile * SPW + sidx;
         const bool valid = b < p.B;
-        const T* xrow = p.x + (valid ? b : p.B - 1) * p.ldx;
+        const int64_t bc = valid ? b : p.B - 1;
+        const T* xrow = ENC == 0 ? p.x + bc * p.ldx : nullptr;
+        const T* u0row = ENC != 0 && p.u0 ? p.u0 + bc * p.ldu0 : nullptr;
+        const T* u1row = ENC != 0 ? p.u1 + bc * p.ldu1 : nullptr;
+
+        auto load_angles = [&](int k, T(&th)[NQ]) {
+            if constexpr (ENC == 0) {
+#pragma unroll
+                for (int q = 0; q < NQ; ++q) th[q] = __ldg(xrow + (int64_t)k * NQ + q);
+            } else {
+                const T* ur = k < p.K0 ? u0row : u1row;
+#pragma unroll
+                for (int q = 0; q < NQ; ++q) {
+                    const int col = k * NQ + q;
+                    const T u = __ldg(ur + __ldg(p.uidx + col));
+                    th[q] = fma_(u, __ldg(p.fw + col), p.fb ? __ldg(p.fb + col) : T(0));
+                }
+            }
+        };
 
         State ps;
         init_zero_state(ps, sub == 0);
@@ -495,16 +527,14 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) hea_reg_kernel(const HeaP
         {
             int s = 0;
             T th[NQ];
-#pragma unroll
-            for (int q = 0; q < NQ; ++q) th[q] = __ldg(xrow + q);
+            load_angles(0, th);
             for (int k = 0; k < p.K; ++k) {
                 T thn[NQ];
-                const int kn = k + 1 < p.K ? k + 1 : k;
-#pragma unroll
-                for (int q = 0; q < NQ; ++q) thn[q] = __ldg(xrow + (int64_t)kn * NQ + q);   // prefetch next block
+                load_angles(k + 1 < p.K ? k + 1 : k, thn);                       // prefetch next block
                 const int d = __ldg(p.depth + k);
 #pragma unroll 1
                 for (int j = 0; j < d; ++j, ++s) {
+                    if constexpr (SYNC_WARPS) __syncthreads();
                     const Vec4<T>* uc = p.ucoef + (int64_t)s * NQ;
                     static_for<NQ>([&](auto Qc) {
                         constexpr int Q = decltype(Qc)::value;
@@ -526,33 +556,37 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) hea_reg_kernel(const HeaP
         T e = real_dot(ps, lm);
 #pragma unroll
         for (int m = 1; m < (1 << LQ); m <<= 1) e += shfl_xor_(e, m);
-        if (valid && sub == 0) p.out[b] = e;
+        if (valid && sub == 0 && p.out) p.out[b] = e;
 
         if constexpr (GRAD) {
             // ---------------- reverse (adjoint) sweep ----------------
             T g = T(0);
-            if (valid) {
-                if (p.target) {   // fused MSE: g = dL/dout for L = gscale/2 * sum (out + bias - y)^2
-                    g = p.gscale * (e + (p.bias ? __ldg(p.bias) : T(0)) - __ldg(p.target + b));
-                    if (sub == 0) p.gbuf[b] = g;
-                } else {
-                    g = __ldg(p.gout + b);
+            if (p.target) {   // fused MSE: g = dL/dout for L = gscale/2 * sum (out + bias - y)^2
+                T resid = T(0);
+                if (valid) {
+                    resid = e + (p.bias ? __ldg(p.bias) : T(0)) - __ldg(p.target + b);
+                    g = p.gscale * resid;
+                    if (sub == 0 && p.gbuf) p.gbuf[b] = g;
                 }
+                T sg = sub == 0 ? g : T(0), sq = sub == 0 ? resid * resid : T(0);
+#pragma unroll
+                for (int m = 16; m >= 1; m >>= 1) { sg += shfl_xor_(sg, m); sq += shfl_xor_(sq, m); }
+                if (lane == 0) { atomicAdd(srow, sg); atomicAdd(srow + 1, sq); }
+            } else if (valid) {
+                g = __ldg(p.gout + b);
             }
             scale_state(lm, g);
             T* gxrow = NEED_GX ? p.gx + (valid ? b : 0) * p.ldgx : nullptr;
             int s = p.S;
             T th[NQ];
-#pragma unroll
-            for (int q = 0; q < NQ; ++q) th[q] = __ldg(xrow + (int64_t)(p.K - 1) * NQ + q);
+            load_angles(p.K - 1, th);
             for (int k = p.K - 1; k >= 0; --k) {
                 T thn[NQ];
-                const int kn = k > 0 ? k - 1 : 0;
-#pragma unroll
-                for (int q = 0; q < NQ; ++q) thn[q] = __ldg(xrow + (int64_t)kn * NQ + q);
+                load_angles(k > 0 ? k - 1 : 0, thn);
                 const int d = __ldg(p.depth + k);
 #pragma unroll 1
                 for (int j = d - 1; j >= 0; --j) {
+                    if constexpr (SYNC_WARPS) __syncthreads();
                     --s;
                     const Vec4<T>* uc = p.ucoef + (int64_t)s * NQ;
                     const Vec4<T>* rc = p.rcoef + (int64_t)s * NQ;
@@ -561,14 +595,19 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) hea_reg_kernel(const HeaP
                     T mv[VP];
 #pragma unroll
                     for (int i = 0; i < VP; ++i) mv[i] = 0;
+                    T fv[FREQ_GRAD ? FVP : 1];
+                    if constexpr (FREQ_GRAD) {
+#pragma unroll
+                        for (int i = 0; i < FVP; ++i) fv[i] = 0;
+                    }
                     static_for<NQ>([&](auto Qc) {
                         constexpr int Q = NQ - 1 - decltype(Qc)::value;
                         const Vec4<T> u = ldg4(uc + Q);
                         T ar = u.x, ai = u.y, br = u.z, bi = u.w;
                         if (j == 0) fold_rx_coef(u, th[Q], ar, ai, br, bi);
                         bwd_group<Q>(ps, lm, ar, ai, br, bi, lane, mv[3 * Q], mv[3 * Q + 1], mv[3 * Q + 2]);
-                        if constexpr (NEED_GX) {
-                            if (j == 0) {   // dL/dx of the folded RX from the three moments
+                        if constexpr (WANT_GX) {
+                            if (j == 0) {   // dL/dtheta of the folded RX from the three moments
                                 T mx = mv[3 * Q], my = mv[3 * Q + 1], mz = mv[3 * Q + 2];
 #pragma unroll
                                 for (int m = 1; m < (1 << LQ); m <<= 1) {
@@ -576,12 +615,27 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) hea_reg_kernel(const HeaP
                                 }
                                 const Vec4<T> r = ldg4(rc + Q);
                                 const T gxv = fma_(r.z, mz, fma_(r.y, my, r.x * mx));
-                                if (valid && sub == 0) gxrow[(int64_t)k * NQ + Q] = gxv;
+                                if constexpr (NEED_GX) {
+                                    if (valid && sub == 0) gxrow[(int64_t)k * NQ + Q] = gxv;
+                                }
+                                if constexpr (FREQ_GRAD) {   // theta = fw*u + fb  =>  d/dfw = gx*u, d/dfb = gx
+                                    const int col = k * NQ + Q;
+                                    const T uval = __ldg((k < p.K0 ? u0row : u1row) + __ldg(p.uidx + col));
+                                    const T gq = sub == 0 ? gxv : T(0);      // invalid samples carry g = 0
+                                    fv[2 * Q] = gq * uval;
+                                    fv[2 * Q + 1] = gq;
+                                }
                             }
                         }
                     });
                     const T tot = butterfly_reduce<T, VP>(mv, lane);
                     if ((lane & (32 / VP - 1)) == 0) atomicAdd(mrow + (int64_t)s * VP + lane / (32 / VP), tot);
+                    if constexpr (FREQ_GRAD) {
+                        if (j == 0) {
+                            const T ft = butterfly_reduce<T, FVP>(fv, lane);
+                            if ((lane & (32 / FVP - 1)) == 0) atomicAdd(frow + (int64_t)k * FVP + lane / (32 / FVP), ft);
+                        }
+                    }
                 }
 #pragma unroll
                 for (int q = 0; q < NQ; ++q) th[q] = thn[q];

@@ -32,13 +32,14 @@ constexpr int kMaxQubits = 24;
 struct DepthPack { unsigned char d[kMaxBlocks]; };
 
 // ---------------------------------------------------------------------------------------------
-// prep: per-(sublayer, qubit) gate tables, Hamiltonian diagonal, depth array, zeroed partial sums
+// prep: per-(sublayer, qubit) gate tables, Hamiltonian diagonal, depth array, column -> source-row
+// index table of the fused encoding, zeroed partial sums
 // ---------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void prep_kernel(const T* __restrict__ w, int n, int S, int K, DepthPack dp,
                             Vec4<T>* ucoef, Vec4<T>* rcoef, int* depth,
                             T* hdiag, const T* ham_diag, int diag_order, double offset, double coeff,
-                            T* mpart, int64_t mpart_len) {
+                            T* mpart, int64_t mpart_len, int* uidx, int K0, int in0, int in1) {
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t nth = (int64_t)gridDim.x * blockDim.x;
     for (int64_t t = tid; t < (int64_t)S * n; t += nth) {
@@ -70,6 +71,13 @@ __global__ void prep_kernel(const T* __restrict__ w, int n, int S, int K, DepthP
         rcoef[t] = r;
     }
     for (int64_t t = tid; t < K; t += nth) depth[t] = dp.d[t];
+    if (uidx) {
+        for (int64_t c = tid; c < (int64_t)n * K; c += nth) {
+            const int k = (int)(c / n);
+            const int64_t local = k < K0 ? c : c - (int64_t)K0 * n;
+            uidx[c] = (int)(local % (k < K0 ? in0 : in1));
+        }
+    }
     const int64_t N = (int64_t)1 << n;
     for (int64_t k = tid; k < N; k += nth) {
         if (ham_diag) {
@@ -93,7 +101,7 @@ __global__ void prep_kernel(const T* __restrict__ w, int n, int S, int K, DepthP
 //                           da = cos(b) mY - sin(b) (cos(c) mX - sin(c) mZ)
 // ---------------------------------------------------------------------------------------------
 template <typename T>
-__global__ void finalize_kernel(const T* __restrict__ mpart, int rows, int S, int VP, int n,
+__global__ void finalize_kernel(const T* __restrict__ mpart, int rows, int64_t rowlen, int VP, int n,
                                 const T* __restrict__ w, T* __restrict__ grad_w) {
     extern __shared__ double sm[];   // [RG][VP]
     const int s = blockIdx.x;
@@ -101,7 +109,7 @@ __global__ void finalize_kernel(const T* __restrict__ mpart, int rows, int S, in
     const int slot = threadIdx.x % VP, rg = threadIdx.x / VP;
     if (rg < RG) {
         double acc = 0.0;
-        for (int r = rg; r < rows; r += RG) acc += (double)mpart[((int64_t)r * S + s) * VP + slot];
+        for (int r = rg; r < rows; r += RG) acc += (double)mpart[(int64_t)r * rowlen + (int64_t)s * VP + slot];
         sm[rg * VP + slot] = acc;
     }
     __syncthreads();
@@ -121,6 +129,38 @@ __global__ void finalize_kernel(const T* __restrict__ mpart, int rows, int S, in
         grad_w[((int64_t)s * 3 + 0) * n + q] = (T)(Cb * m[1] - Sb * (Cc * m[0] - Sc * m[2]));
         grad_w[((int64_t)s * 3 + 1) * n + q] = (T)(Cc * m[2] + Sc * m[0]);
         grad_w[((int64_t)s * 3 + 2) * n + q] = (T)m[1];
+    }
+}
+
+// frequency-layer gradients and the two scalar sums of the fused-encoding training kernels:
+// block k < K: slots (2q, 2q+1) of block k -> grad_fw / grad_fb[k*n+q];  block K: [sum g, sum resid^2]
+template <typename T>
+__global__ void finalize_enc_kernel(const T* __restrict__ mpart, int rows, int64_t rowlen, int64_t off, int FVP,
+                                    int n, int K, T* __restrict__ grad_fw, T* __restrict__ grad_fb,
+                                    T* __restrict__ sums) {
+    __shared__ double sm[256];
+    const int k = blockIdx.x;
+    const int width = k < K ? FVP : 2;
+    const int64_t base = off + (k < K ? (int64_t)k * FVP : (int64_t)K * FVP);
+    const int RG = blockDim.x / width;
+    const int slot = threadIdx.x % width, rg = threadIdx.x / width;
+    double acc = 0.0;
+    if (rg < RG)
+        for (int r = rg; r < rows; r += RG) acc += (double)mpart[(int64_t)r * rowlen + base + slot];
+    sm[threadIdx.x] = rg < RG ? acc : 0.0;
+    __syncthreads();
+    if (threadIdx.x < width) {
+        double tot = 0.0;
+        for (int g = 0; g < RG; ++g) tot += sm[g * width + threadIdx.x];
+        if (k < K) {
+            const int q = threadIdx.x >> 1;
+            if (q < n) {
+                if ((threadIdx.x & 1) == 0) { if (grad_fw) grad_fw[(int64_t)k * n + q] = (T)tot; }
+                else if (grad_fb) grad_fb[(int64_t)k * n + q] = (T)tot;
+            }
+        } else if (sums) {
+            sums[threadIdx.x] = (T)tot;
+        }
     }
 }
 
@@ -169,10 +209,12 @@ bool device_info(int* dev_out, DeviceInfo* info) {
     return true;
 }
 
+constexpr int kModes = 6;   // see hea_reg_inst.cuh
+
 RegLaunchInfo reg_info_cached(int dev, int dtype, int nl, int lq, int mode) {
     static std::mutex mu;
-    static RegLaunchInfo cache[64][2][6][6][3];
-    static bool have[64][2][6][6][3];
+    static RegLaunchInfo cache[64][2][6][6][kModes];
+    static bool have[64][2][6][6][kModes];
     std::lock_guard<std::mutex> lk(mu);
     if (!have[dev][dtype][nl][lq][mode]) {
         cache[dev][dtype][nl][lq][mode] = dtype == 0 ? reg_info_f32(nl, lq, mode) : reg_info_f64(nl, lq, mode);
@@ -182,17 +224,18 @@ RegLaunchInfo reg_info_cached(int dev, int dtype, int nl, int lq, int mode) {
 }
 
 inline size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
+inline bool mode_is_grad(int mode) { return mode == 1 || mode == 2 || mode == 4 || mode == 5; }
+inline bool mode_is_enc(int mode) { return mode >= 3; }
 
 struct Plan {
     int tier = -1;            // 0 register, 1 shared-memory, 2 HBM-streamed
     int nl = 0, lq = 0;
-    int grid = 0, rows = 0, vp = 0, S = 0;
+    int grid = 0, rows = 0, vp = 0, fvp = 0, S = 0;
     GenericPlan gp{};
-    size_t off_u = 0, off_r = 0, off_h = 0, off_d = 0, off_m = 0, off_state = 0, total = 0;
-    int64_t mpart_len = 0;
+    size_t off_u = 0, off_r = 0, off_h = 0, off_d = 0, off_i = 0, off_m = 0, off_state = 0, total = 0;
+    int64_t rowlen = 0, mpart_len = 0;
 };
 
-// mode: 0 forward, 1 forward+backward (+dL/dx), 2 forward+backward (no dL/dx)
 int make_plan(int64_t B, int n, int K, const int* depth, int dtype, int mode, Plan* pl) {
     if (B < 0) return fail(QON_ERR_BAD_ARG, "B must be >= 0 (got %lld)", (long long)B);
     if (n < 1 || n > kMaxQubits) return fail(QON_ERR_UNSUPPORTED, "n must be in [1, %d] (got %d)", kMaxQubits, n);
@@ -209,6 +252,7 @@ int make_plan(int64_t B, int n, int K, const int* depth, int dtype, int mode, Pl
     DeviceInfo di;
     if (!device_info(&dev, &di)) return fail(QON_ERR_NO_DEVICE, "no usable CUDA device");
     const size_t es = dtype == QON_F32 ? 4 : 8;
+    const bool grad = mode_is_grad(mode);
     pl->S = (int)S;
     const int max_local = dtype == QON_F32 ? 5 : 4;
     if (n <= max_local + 5) {
@@ -216,7 +260,9 @@ int make_plan(int64_t B, int n, int K, const int* depth, int dtype, int mode, Pl
         pl->nl = n <= max_local ? n : max_local;
         pl->lq = n - pl->nl;
         RegLaunchInfo ri = reg_info_cached(dev, dtype, pl->nl, pl->lq, mode);
-        if (!ri.ok) return fail(QON_ERR_UNSUPPORTED, "register-tier kernel (nl=%d, lq=%d) unavailable", pl->nl, pl->lq);
+        if (!ri.ok)
+            return fail(QON_ERR_UNSUPPORTED, "register-tier kernel (n=%d, lanes 2^%d, mode %d) is not built%s", n,
+                        pl->lq, mode, mode_is_enc(mode) ? " (fused encoding needs n <= 5 in fp32, n <= 4 in fp64)" : "");
         const int warps = ri.threads / 32;
         const int64_t spw = 32 >> pl->lq;
         const int64_t tiles = (B + spw - 1) / spw;
@@ -227,7 +273,10 @@ int make_plan(int64_t B, int n, int K, const int* depth, int dtype, int mode, Pl
         pl->grid = (int)grid;
         pl->rows = (int)grid * warps;
         pl->vp = moment_slots(n);
+        pl->fvp = freq_slots(n);
     } else {
+        if (mode_is_enc(mode))
+            return fail(QON_ERR_UNSUPPORTED, "fused encoding is built for the register tier only (n=%d)", n);
         pl->gp = generic_plan(n, dtype, mode);
         if (!pl->gp.state_global && pl->gp.blocks_per_sm < 1)
             return fail(QON_ERR_UNSUPPORTED, "generic kernel does not fit for n=%d", n);
@@ -238,73 +287,113 @@ int make_plan(int64_t B, int n, int K, const int* depth, int dtype, int mode, Pl
         pl->grid = (int)grid;
         pl->rows = (int)grid;
         pl->vp = (3 * n + 3) / 4 * 4;
+        pl->fvp = 0;
     }
     size_t off = 0;
     pl->off_u = off; off = align_up(off + (size_t)S * n * 4 * es);
     pl->off_r = off; off = align_up(off + (size_t)S * n * 4 * es);
     pl->off_h = off; off = align_up(off + ((size_t)1 << n) * es);
     pl->off_d = off; off = align_up(off + (size_t)K * sizeof(int));
+    pl->off_i = off; off = align_up(off + (size_t)K * n * sizeof(int));
     pl->off_m = off;
-    pl->mpart_len = mode ? (int64_t)pl->rows * S * pl->vp : 0;
+    pl->rowlen = (int64_t)S * pl->vp + (int64_t)K * pl->fvp + 4;
+    pl->mpart_len = grad ? (int64_t)pl->rows * pl->rowlen : 0;
     off = align_up(off + (size_t)pl->mpart_len * es);
     pl->off_state = off;
-    if (pl->tier == 2) off = align_up(off + (size_t)pl->grid * (mode ? 4 : 2) * ((size_t)1 << n) * es);
+    if (pl->tier == 2) off = align_up(off + (size_t)pl->grid * (grad ? 4 : 2) * ((size_t)1 << n) * es);
     pl->total = off;
     return 0;
 }
 
+struct Job {
+    // circuit
+    const void* w = nullptr; void* out = nullptr;
+    int64_t B = 0; int n = 0, K = 0; const int* depth = nullptr;
+    const void* ham_diag = nullptr; int diag_order = 0; double offset = 0, coeff = 0; int ham_kind = 0; int dtype = 0;
+    void* ws = nullptr; size_t ws_bytes = 0; void* stream = nullptr;
+    // angles given
+    const void* x = nullptr; int64_t ldx = 0;
+    // fused encoding
+    bool enc = false;
+    const void *u0 = nullptr, *u1 = nullptr; int64_t ldu0 = 0, ldu1 = 0; int in0 = 0, in1 = 0, K0 = 0;
+    const void *fw = nullptr, *fb = nullptr;
+    void *grad_fw = nullptr, *grad_fb = nullptr, *sums = nullptr;
+    // gradients
+    bool grad = false;
+    const void *grad_out = nullptr, *target = nullptr, *bias = nullptr; double gscale = 0; void* gbuf = nullptr;
+    void* grad_x = nullptr; int64_t ldgx = 0; void* grad_w = nullptr;
+};
+
+int job_mode(const Job& j) {
+    if (j.enc) return !j.grad ? 3 : ((j.grad_fw || j.grad_fb) ? 5 : 4);
+    return !j.grad ? 0 : (j.grad_x ? 1 : 2);
+}
+
 template <typename T>
-int run(const void* x, int64_t ldx, const void* w, const void* grad_out, const void* target, const void* bias,
-        double gscale, void* gbuf, void* out, void* grad_x, int64_t ldgx,
-        void* grad_w, int64_t B, int n, int K, const int* depth, const void* ham_diag, int diag_order,
-        double offset, double coeff, int ham_kind, int dtype, void* ws, size_t ws_bytes, void* stream, bool grad) {
-    const int mode = !grad ? 0 : (grad_x ? 1 : 2);
+int run(const Job& j) {
+    const int mode = job_mode(j);
+    const int n = j.n, K = j.K;
     Plan pl;
-    if (int rc = make_plan(B, n, K, depth, dtype, mode, &pl)) return rc;
-    if (!x || !w || !out) return fail(QON_ERR_BAD_ARG, "x, w and out must be non-NULL");
-    if (grad && !grad_w) return fail(QON_ERR_BAD_ARG, "grad_w must be non-NULL");
-    if (grad && !grad_out && !target) return fail(QON_ERR_BAD_ARG, "grad_out (or target) must be non-NULL");
-    if (target && !gbuf) return fail(QON_ERR_BAD_ARG, "grad_out_written must be non-NULL when target is given");
-    if (ldx < (int64_t)n * K) return fail(QON_ERR_BAD_ARG, "ldx (%lld) < n*K (%d)", (long long)ldx, n * K);
-    if (grad_x && ldgx < (int64_t)n * K) return fail(QON_ERR_BAD_ARG, "ldgx (%lld) < n*K (%d)", (long long)ldgx, n * K);
-    if (ham_kind < QON_HAM_DIAG || ham_kind > QON_HAM_PAULI_Y) return fail(QON_ERR_BAD_ARG, "bad ham_kind %d", ham_kind);
-    if (ham_diag && ham_kind != QON_HAM_DIAG) return fail(QON_ERR_BAD_ARG, "ham_diag given with a Pauli-X/Y observable");
-    if (diag_order != QON_DIAG_LSB0 && diag_order != QON_DIAG_MSB0) return fail(QON_ERR_BAD_ARG, "bad diag_order %d", diag_order);
-    if (!ws || ws_bytes < pl.total)
-        return fail(QON_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", pl.total, ws_bytes);
-    if ((uintptr_t)ws % 256) return fail(QON_ERR_BAD_ARG, "workspace must be 256-byte aligned");
+    if (int rc = make_plan(j.B, n, K, j.depth, j.dtype, mode, &pl)) return rc;
+    if (!j.w) return fail(QON_ERR_BAD_ARG, "w must be non-NULL");
+    if (!j.enc) {
+        if (!j.x || !j.out) return fail(QON_ERR_BAD_ARG, "x and out must be non-NULL");
+        if (j.ldx < (int64_t)n * K) return fail(QON_ERR_BAD_ARG, "ldx (%lld) < n*K (%d)", (long long)j.ldx, n * K);
+    } else {
+        if (j.K0 < 0 || j.K0 > K) return fail(QON_ERR_BAD_ARG, "K0 (%d) outside [0, K=%d]", j.K0, K);
+        if (!j.fw) return fail(QON_ERR_BAD_ARG, "fw must be non-NULL");
+        if (j.K0 > 0 && (!j.u0 || j.in0 < 1 || j.ldu0 < j.in0)) return fail(QON_ERR_BAD_ARG, "bad source 0 (u0/in0/ldu0)");
+        if (j.K0 < K && (!j.u1 || j.in1 < 1 || j.ldu1 < j.in1)) return fail(QON_ERR_BAD_ARG, "bad source 1 (u1/in1/ldu1)");
+        if (!j.grad && !j.out) return fail(QON_ERR_BAD_ARG, "out must be non-NULL");
+    }
+    if (j.grad && !j.grad_w) return fail(QON_ERR_BAD_ARG, "grad_w must be non-NULL");
+    if (j.grad && !j.grad_out && !j.target) return fail(QON_ERR_BAD_ARG, "grad_out (or target) must be non-NULL");
+    if (j.grad_x && j.ldgx < (int64_t)n * K)
+        return fail(QON_ERR_BAD_ARG, "ldgx (%lld) < n*K (%d)", (long long)j.ldgx, n * K);
+    if (j.ham_kind < QON_HAM_DIAG || j.ham_kind > QON_HAM_PAULI_Y) return fail(QON_ERR_BAD_ARG, "bad ham_kind %d", j.ham_kind);
+    if (j.ham_diag && j.ham_kind != QON_HAM_DIAG) return fail(QON_ERR_BAD_ARG, "ham_diag given with a Pauli-X/Y observable");
+    if (j.diag_order != QON_DIAG_LSB0 && j.diag_order != QON_DIAG_MSB0) return fail(QON_ERR_BAD_ARG, "bad diag_order %d", j.diag_order);
+    if (!j.ws || j.ws_bytes < pl.total)
+        return fail(QON_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", pl.total, j.ws_bytes);
+    if ((uintptr_t)j.ws % 256) return fail(QON_ERR_BAD_ARG, "workspace must be 256-byte aligned");
     const uintptr_t am = sizeof(T) - 1;
-    if (((uintptr_t)x & am) || ((uintptr_t)w & am) || ((uintptr_t)out & am))
-        return fail(QON_ERR_BAD_ARG, "x / w / out must be aligned to the element size");
-    cudaStream_t st = (cudaStream_t)stream;
-    char* base = (char*)ws;
+    if (((uintptr_t)j.x & am) || ((uintptr_t)j.w & am) || ((uintptr_t)j.out & am) || ((uintptr_t)j.u0 & am) ||
+        ((uintptr_t)j.u1 & am))
+        return fail(QON_ERR_BAD_ARG, "device pointers must be aligned to the element size");
+    cudaStream_t st = (cudaStream_t)j.stream;
+    char* base = (char*)j.ws;
     HeaParams<T> p{};
-    p.x = (const T*)x; p.ldx = ldx; p.B = B; p.out = (T*)out;
-    p.gout = (const T*)grad_out; p.gx = (T*)grad_x; p.ldgx = ldgx;
-    p.target = (const T*)target; p.bias = (const T*)bias; p.gbuf = (T*)gbuf; p.gscale = (T)gscale;
+    p.x = (const T*)j.x; p.ldx = j.ldx; p.B = j.B; p.out = (T*)j.out;
+    p.gout = (const T*)j.grad_out; p.gx = (T*)j.grad_x; p.ldgx = j.ldgx;
+    p.target = (const T*)j.target; p.bias = (const T*)j.bias; p.gbuf = (T*)j.gbuf; p.gscale = (T)j.gscale;
     p.ucoef = (const Vec4<T>*)(base + pl.off_u);
     p.rcoef = (const Vec4<T>*)(base + pl.off_r);
     p.hdiag = (const T*)(base + pl.off_h);
     p.depth = (const int*)(base + pl.off_d);
     p.mpart = (T*)(base + pl.off_m);
-    p.K = K; p.S = pl.S; p.pauli = ham_kind; p.offset = (T)offset; p.coeff = (T)coeff;
+    p.rowlen = pl.rowlen;
+    p.K = K; p.S = pl.S; p.pauli = j.ham_kind; p.offset = (T)j.offset; p.coeff = (T)j.coeff;
+    p.u0 = (const T*)j.u0; p.u1 = (const T*)j.u1; p.ldu0 = j.ldu0; p.ldu1 = j.ldu1; p.K0 = j.K0;
+    p.uidx = j.enc ? (const int*)(base + pl.off_i) : nullptr;
+    p.fw = (const T*)j.fw; p.fb = (const T*)j.fb;
 
     DepthPack dp;
     memset(&dp, 0, sizeof dp);
-    for (int k = 0; k < K; ++k) dp.d[k] = (unsigned char)depth[k];
+    for (int k = 0; k < K; ++k) dp.d[k] = (unsigned char)j.depth[k];
     {
         const int64_t work = pl.mpart_len > ((int64_t)1 << n) ? pl.mpart_len : ((int64_t)1 << n);
         int64_t blocks = (work + 255) / 256;
         if (blocks > 1184) blocks = 1184;
         if (blocks < 1) blocks = 1;
-        prep_kernel<T><<<(int)blocks, 256, 0, st>>>((const T*)w, n, pl.S, K, dp, (Vec4<T>*)(base + pl.off_u),
-                                                    (Vec4<T>*)(base + pl.off_r), (int*)(base + pl.off_d),
-                                                    (T*)(base + pl.off_h), (const T*)ham_diag, diag_order, offset,
-                                                    coeff, p.mpart, pl.mpart_len);
+        prep_kernel<T><<<(int)blocks, 256, 0, st>>>(
+            (const T*)j.w, n, pl.S, K, dp, (Vec4<T>*)(base + pl.off_u), (Vec4<T>*)(base + pl.off_r),
+            (int*)(base + pl.off_d), (T*)(base + pl.off_h), (const T*)j.ham_diag, j.diag_order, j.offset, j.coeff,
+            p.mpart, pl.mpart_len, j.enc ? (int*)(base + pl.off_i) : nullptr, j.K0, j.in0 > 0 ? j.in0 : 1,
+            j.in1 > 0 ? j.in1 : 1);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return fail((int)e, "prep launch failed: %s", cudaGetErrorString(e));
     }
-    if (B > 0) {
+    if (j.B > 0) {
         cudaError_t e;
         if (pl.tier == 0) {
             if constexpr (sizeof(T) == 4) e = reg_launch_f32(pl.nl, pl.lq, mode, pl.grid, (const HeaParams<float>&)p, st);
@@ -318,16 +407,37 @@ int run(const void* x, int64_t ldx, const void* w, const void* grad_out, const v
         }
         if (e != cudaSuccess) return fail((int)e, "kernel launch failed: %s", cudaGetErrorString(e));
     }
-    if (grad) {
+    if (j.grad) {
+        const int rows = j.B > 0 ? pl.rows : 0;
         int threads = 256;
         while (threads < pl.vp) threads <<= 1;
         const int RG = threads / pl.vp;
         finalize_kernel<T><<<pl.S, threads, (size_t)RG * pl.vp * sizeof(double), st>>>(
-            p.mpart, B > 0 ? pl.rows : 0, pl.S, pl.vp, n, (const T*)w, (T*)grad_w);
+            p.mpart, rows, pl.rowlen, pl.vp, n, (const T*)j.w, (T*)j.grad_w);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return fail((int)e, "finalize launch failed: %s", cudaGetErrorString(e));
+        if (j.enc && (j.grad_fw || j.grad_fb || j.sums)) {
+            finalize_enc_kernel<T><<<K + 1, 256, 0, st>>>(p.mpart, rows, pl.rowlen, (int64_t)pl.S * pl.vp, pl.fvp, n, K,
+                                                          (T*)j.grad_fw, (T*)j.grad_fb, (T*)j.sums);
+            e = cudaGetLastError();
+            if (e != cudaSuccess) return fail((int)e, "finalize_enc launch failed: %s", cudaGetErrorString(e));
+        }
     }
     return 0;
+}
+
+int dispatch(const Job& j) {
+    if (j.dtype == QON_F32) return run<float>(j);
+    if (j.dtype == QON_F64) return run<double>(j);
+    return fail(QON_ERR_BAD_ARG, "dtype must be QON_F32 or QON_F64");
+}
+
+void fill_common(Job& j, const void* w, void* out, int64_t B, int n, int K, const int* depth, const void* ham_diag,
+                 int diag_order, double off, double coeff, int ham_kind, int dtype, void* ws, size_t ws_bytes,
+                 void* stream) {
+    j.w = w; j.out = out; j.B = B; j.n = n; j.K = K; j.depth = depth; j.ham_diag = ham_diag; j.diag_order = diag_order;
+    j.offset = off; j.coeff = coeff; j.ham_kind = ham_kind; j.dtype = dtype; j.ws = ws; j.ws_bytes = ws_bytes;
+    j.stream = stream;
 }
 
 }  // namespace
@@ -342,13 +452,17 @@ int qon_abi_version(void) { return QON_ABI_VERSION; }
 const char* qon_last_error(void) { return g_err.c_str(); }
 
 size_t qon_workspace_bytes(int64_t B, int n, int K, const int* depth_per_block, int dtype, int need_grad) {
-    Plan pl;
-    if (make_plan(B, n, K, depth_per_block, dtype, need_grad ? 1 : 0, &pl)) return 0;
-    size_t total = pl.total;
-    if (need_grad) {   // with / without dL/dx are different kernels (different occupancy -> different row count)
-        Plan pl2;
-        if (make_plan(B, n, K, depth_per_block, dtype, 2, &pl2)) return 0;
-        if (pl2.total > total) total = pl2.total;
+    // the variants of one entry-point family are different kernels (different occupancy -> different number
+    // of partial rows); report the maximum so one workspace serves them all
+    const int fwd_modes[] = {0, 3}, grad_modes[] = {1, 2, 4, 5};
+    const int* modes = need_grad ? grad_modes : fwd_modes;
+    const int count = need_grad ? 4 : 2;
+    size_t total = 0;
+    for (int i = 0; i < count; ++i) {
+        Plan pl;
+        const int rc = make_plan(B, n, K, depth_per_block, dtype, modes[i], &pl);
+        if (rc == 0) { if (pl.total > total) total = pl.total; }
+        else if (modes[i] < 3) return 0;          // the plain variants must plan; fused encoding is optional
     }
     return total;
 }
@@ -364,26 +478,23 @@ int qon_plan_tier(int64_t B, int n, int dtype, int need_grad, int* lanes_log2) {
 int qon_hea_forward(const void* x, int64_t ldx, const void* w, void* out, int64_t B, int n, int K,
                     const int* depth_per_block, const void* ham_diag, int diag_order, double ham_offset,
                     double ham_coeff, int ham_kind, int dtype, void* workspace, size_t workspace_bytes, void* stream) {
-    if (dtype == QON_F32)
-        return run<float>(x, ldx, w, nullptr, nullptr, nullptr, 0.0, nullptr, out, nullptr, 0, nullptr, B, n, K, depth_per_block, ham_diag, diag_order,
-                          ham_offset, ham_coeff, ham_kind, dtype, workspace, workspace_bytes, stream, false);
-    if (dtype == QON_F64)
-        return run<double>(x, ldx, w, nullptr, nullptr, nullptr, 0.0, nullptr, out, nullptr, 0, nullptr, B, n, K, depth_per_block, ham_diag, diag_order,
-                           ham_offset, ham_coeff, ham_kind, dtype, workspace, workspace_bytes, stream, false);
-    return fail(QON_ERR_BAD_ARG, "dtype must be QON_F32 or QON_F64");
+    Job j;
+    fill_common(j, w, out, B, n, K, depth_per_block, ham_diag, diag_order, ham_offset, ham_coeff, ham_kind, dtype,
+                workspace, workspace_bytes, stream);
+    j.x = x; j.ldx = ldx;
+    return dispatch(j);
 }
 
 int qon_hea_forward_backward(const void* x, int64_t ldx, const void* w, const void* grad_out, void* out, void* grad_x,
                              int64_t ldgx, void* grad_w, int64_t B, int n, int K, const int* depth_per_block,
                              const void* ham_diag, int diag_order, double ham_offset, double ham_coeff, int ham_kind,
                              int dtype, void* workspace, size_t workspace_bytes, void* stream) {
-    if (dtype == QON_F32)
-        return run<float>(x, ldx, w, grad_out, nullptr, nullptr, 0.0, nullptr, out, grad_x, ldgx, grad_w, B, n, K, depth_per_block, ham_diag, diag_order,
-                          ham_offset, ham_coeff, ham_kind, dtype, workspace, workspace_bytes, stream, true);
-    if (dtype == QON_F64)
-        return run<double>(x, ldx, w, grad_out, nullptr, nullptr, 0.0, nullptr, out, grad_x, ldgx, grad_w, B, n, K, depth_per_block, ham_diag, diag_order,
-                           ham_offset, ham_coeff, ham_kind, dtype, workspace, workspace_bytes, stream, true);
-    return fail(QON_ERR_BAD_ARG, "dtype must be QON_F32 or QON_F64");
+    if (!grad_out) return fail(QON_ERR_BAD_ARG, "grad_out must be non-NULL");
+    Job j;
+    fill_common(j, w, out, B, n, K, depth_per_block, ham_diag, diag_order, ham_offset, ham_coeff, ham_kind, dtype,
+                workspace, workspace_bytes, stream);
+    j.x = x; j.ldx = ldx; j.grad = true; j.grad_out = grad_out; j.grad_x = grad_x; j.ldgx = ldgx; j.grad_w = grad_w;
+    return dispatch(j);
 }
 
 int qon_hea_mse_forward_backward(const void* x, int64_t ldx, const void* w, const void* target, const void* bias,
@@ -392,15 +503,43 @@ int qon_hea_mse_forward_backward(const void* x, int64_t ldx, const void* w, cons
                                  const void* ham_diag, int diag_order, double ham_offset, double ham_coeff, int ham_kind,
                                  int dtype, void* workspace, size_t workspace_bytes, void* stream) {
     if (!target) return fail(QON_ERR_BAD_ARG, "target must be non-NULL");
-    if (dtype == QON_F32)
-        return run<float>(x, ldx, w, nullptr, target, bias, grad_scale, grad_out_written, out, grad_x, ldgx, grad_w, B, n,
-                          K, depth_per_block, ham_diag, diag_order, ham_offset, ham_coeff, ham_kind, dtype, workspace,
-                          workspace_bytes, stream, true);
-    if (dtype == QON_F64)
-        return run<double>(x, ldx, w, nullptr, target, bias, grad_scale, grad_out_written, out, grad_x, ldgx, grad_w, B,
-                           n, K, depth_per_block, ham_diag, diag_order, ham_offset, ham_coeff, ham_kind, dtype, workspace,
-                           workspace_bytes, stream, true);
-    return fail(QON_ERR_BAD_ARG, "dtype must be QON_F32 or QON_F64");
+    if (!grad_out_written) return fail(QON_ERR_BAD_ARG, "grad_out_written must be non-NULL");
+    Job j;
+    fill_common(j, w, out, B, n, K, depth_per_block, ham_diag, diag_order, ham_offset, ham_coeff, ham_kind, dtype,
+                workspace, workspace_bytes, stream);
+    j.x = x; j.ldx = ldx; j.grad = true; j.target = target; j.bias = bias; j.gscale = grad_scale;
+    j.gbuf = grad_out_written; j.grad_x = grad_x; j.ldgx = ldgx; j.grad_w = grad_w;
+    return dispatch(j);
+}
+
+int qon_encoded_forward(const void* u0, int64_t ldu0, int in0, int K0, const void* u1, int64_t ldu1, int in1,
+                        const void* fw, const void* fb, const void* w, void* out, int64_t B, int n, int K,
+                        const int* depth_per_block, const void* ham_diag, int diag_order, double ham_offset,
+                        double ham_coeff, int ham_kind, int dtype, void* workspace, size_t workspace_bytes,
+                        void* stream) {
+    Job j;
+    fill_common(j, w, out, B, n, K, depth_per_block, ham_diag, diag_order, ham_offset, ham_coeff, ham_kind, dtype,
+                workspace, workspace_bytes, stream);
+    j.enc = true; j.u0 = u0; j.ldu0 = ldu0; j.in0 = in0; j.K0 = K0; j.u1 = u1; j.ldu1 = ldu1; j.in1 = in1;
+    j.fw = fw; j.fb = fb;
+    return dispatch(j);
+}
+
+int qon_encoded_mse_step(const void* u0, int64_t ldu0, int in0, int K0, const void* u1, int64_t ldu1, int in1,
+                         const void* fw, const void* fb, const void* w, const void* target, const void* bias,
+                         double grad_scale, void* out, void* grad_w, void* grad_fw, void* grad_fb, void* sums,
+                         int64_t B, int n, int K, const int* depth_per_block, const void* ham_diag, int diag_order,
+                         double ham_offset, double ham_coeff, int ham_kind, int dtype, void* workspace,
+                         size_t workspace_bytes, void* stream) {
+    if (!target) return fail(QON_ERR_BAD_ARG, "target must be non-NULL");
+    if (!sums) return fail(QON_ERR_BAD_ARG, "sums must be non-NULL");
+    Job j;
+    fill_common(j, w, out, B, n, K, depth_per_block, ham_diag, diag_order, ham_offset, ham_coeff, ham_kind, dtype,
+                workspace, workspace_bytes, stream);
+    j.enc = true; j.u0 = u0; j.ldu0 = ldu0; j.in0 = in0; j.K0 = K0; j.u1 = u1; j.ldu1 = ldu1; j.in1 = in1;
+    j.fw = fw; j.fb = fb; j.grad = true; j.target = target; j.bias = bias; j.gscale = grad_scale;
+    j.grad_w = grad_w; j.grad_fw = grad_fw; j.grad_fb = grad_fb; j.sums = sums;
+    return dispatch(j);
 }
 
 double qon_measure_fp32_peak_tflops(int iters, void* stream) {

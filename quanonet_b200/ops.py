@@ -208,3 +208,108 @@ def _(x, weights, target, bias, grad_scale, n_wires, depth_per_block, ham_diag, 
       ham_kind, need_grad_x):
     gx = x.new_empty(x.shape if need_grad_x else (0,))
     return x.new_empty((x.shape[0], 1)), x.new_empty((x.shape[0],)), gx, torch.empty_like(weights)
+
+
+# ------------------------------------------------------------------------------------------------
+# fused encoding: frequency layers evaluated inside the kernel (x / grad_x never materialised)
+# ------------------------------------------------------------------------------------------------
+def _enc_args(u0, u1, fw, fb, K0, n_wires, depth_per_block):
+    if not u1.is_cuda:
+        raise RuntimeError("quanonet encoded ops run on CUDA tensors only (there is no CPU fallback)")
+    if u1.dtype not in _DTYPES:
+        raise TypeError(f"inputs must be float32 or float64, got {u1.dtype}")
+    E = n_wires * len(depth_per_block)
+    if fw.numel() != E or (fb is not None and fb.numel() != E):
+        raise ValueError(f"fw / fb must have n*K = {E} entries")
+    if u0 is None and K0 != 0:
+        raise ValueError("K0 > 0 needs a source-0 input")
+    u1c, ld1 = _rowmajor(u1)
+    if u0 is not None:
+        u0c, ld0 = _rowmajor(u0.to(u1.dtype))
+        head = [u0c.data_ptr(), ld0, int(u0c.shape[1]), int(K0)]
+    else:
+        u0c, head = None, [None, 0, 0, 0]
+    fwc = fw.to(u1.dtype).contiguous()
+    fbc = None if fb is None else fb.to(u1.dtype).contiguous()
+    head += [u1c.data_ptr(), ld1, int(u1c.shape[1]), fwc.data_ptr(), None if fbc is None else fbc.data_ptr()]
+    return head, (u0c, u1c, fwc, fbc)
+
+
+@torch.library.custom_op("quanonet::encoded_expval", mutates_args=())
+def encoded_expval(u0: Optional[torch.Tensor], u1: torch.Tensor, fw: torch.Tensor, fb: Optional[torch.Tensor],
+                   K0: int, weights: torch.Tensor, n_wires: int, depth_per_block: List[int],
+                   ham_diag: Optional[torch.Tensor], diag_order: int, ham_offset: float, ham_coeff: float,
+                   ham_kind: int) -> torch.Tensor:
+    """Forward of the whole model body (frequency layers + circuit) in one kernel: ``qon_encoded_forward``."""
+    lib = _lib.load()
+    B = u1.shape[0]
+    out = torch.empty((B, 1), dtype=u1.dtype, device=u1.device)
+    if B == 0:
+        return out
+    with torch.cuda.device(u1.device):
+        head, keep = _enc_args(u0, u1, fw, fb, K0, n_wires, depth_per_block)
+        code = _DTYPES[u1.dtype]
+        wc = weights.to(u1.dtype).contiguous()
+        hd = None if ham_diag is None else ham_diag.to(dtype=u1.dtype, device=u1.device).contiguous()
+        depth = _lib.int_array(depth_per_block)
+        ws, nbytes = _workspace(B, n_wires, depth, code, False, u1.device)
+        rc = lib.qon_encoded_forward(*head, wc.data_ptr(), out.data_ptr(), B, n_wires, len(depth_per_block), depth,
+                                     None if hd is None else hd.data_ptr(), diag_order, ham_offset, ham_coeff, ham_kind,
+                                     code, ws.data_ptr(), nbytes, torch.cuda.current_stream(u1.device).cuda_stream)
+        _lib.check(rc, "qon_encoded_forward")
+    return out
+
+
+@encoded_expval.register_fake
+def _(u0, u1, fw, fb, K0, weights, n_wires, depth_per_block, ham_diag, diag_order, ham_offset, ham_coeff, ham_kind):
+    return u1.new_empty((u1.shape[0], 1))
+
+
+@torch.library.custom_op("quanonet::encoded_mse_step", mutates_args=())
+def encoded_mse_step(u0: Optional[torch.Tensor], u1: torch.Tensor, fw: torch.Tensor, fb: Optional[torch.Tensor],
+                     K0: int, weights: torch.Tensor, target: torch.Tensor, bias: Optional[torch.Tensor],
+                     grad_scale: float, n_wires: int, depth_per_block: List[int], ham_diag: Optional[torch.Tensor],
+                     diag_order: int, ham_offset: float, ham_coeff: float, ham_kind: int,
+                     need_freq_grad: bool) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
+    """``qon_encoded_mse_step``: returns (grad_w (S,3,n), grad_fw (E,) or empty, grad_fb (E,) or empty,
+    sums (2,) = [sum g, sum squared residual])."""
+    lib = _lib.load()
+    B = u1.shape[0]
+    dt, dev = u1.dtype, u1.device
+    E = n_wires * len(depth_per_block)
+    grad_w = torch.empty(weights.shape, dtype=dt, device=dev)
+    gfw = torch.empty((E,) if need_freq_grad else (0,), dtype=dt, device=dev)
+    gfb = torch.empty((E,) if need_freq_grad else (0,), dtype=dt, device=dev)
+    sums = torch.empty((2,), dtype=dt, device=dev)
+    with torch.cuda.device(dev):
+        head, keep = _enc_args(u0, u1, fw, fb, K0, n_wires, depth_per_block)
+        code = _DTYPES[dt]
+        wc = weights.to(dt).contiguous()
+        y = target.to(dt).reshape(-1).contiguous()
+        if y.numel() != B:
+            raise ValueError(f"target must have B = {B} elements, got {y.numel()}")
+        bc = None if bias is None else bias.to(dt).reshape(-1).contiguous()
+        hd = None if ham_diag is None else ham_diag.to(dtype=dt, device=dev).contiguous()
+        depth = _lib.int_array(depth_per_block)
+        ws, nbytes = _workspace(B, n_wires, depth, code, True, dev)
+        rc = lib.qon_encoded_mse_step(
+            *head, wc.data_ptr(), y.data_ptr(), None if bc is None else bc.data_ptr(), float(grad_scale), None,
+            grad_w.data_ptr(), gfw.data_ptr() if need_freq_grad else None, gfb.data_ptr() if need_freq_grad else None,
+            sums.data_ptr(), B, n_wires, len(depth_per_block), depth, None if hd is None else hd.data_ptr(),
+            diag_order, ham_offset, ham_coeff, ham_kind, code, ws.data_ptr(), nbytes,
+            torch.cuda.current_stream(dev).cuda_stream)
+        _lib.check(rc, "qon_encoded_mse_step")
+    return grad_w, gfw, gfb, sums
+
+
+@encoded_mse_step.register_fake
+def _(u0, u1, fw, fb, K0, weights, target, bias, grad_scale, n_wires, depth_per_block, ham_diag, diag_order,
+      ham_offset, ham_coeff, ham_kind, need_freq_grad):
+    E = n_wires * len(depth_per_block)
+    g = u1.new_empty((E,) if need_freq_grad else (0,))
+    return torch.empty_like(weights), g, u1.new_empty(g.shape), u1.new_empty((2,))
+
+
+def encoded_supported(n_wires: int, dtype=torch.float32) -> bool:
+    """Fused-encoding kernels exist for one-thread-per-sample layouts: n <= 5 (fp32) / n <= 4 (fp64)."""
+    return n_wires <= (5 if dtype == torch.float32 else 4)

@@ -59,7 +59,7 @@ class DataParallelTrainer:
     """
 
     def __init__(self, model: nn.Module, lr: float = 1e-3, optimizer: str = "adam", optimizer_kwargs=None,
-                 process_group=None, kernel_fn: Optional[Callable] = None):
+                 process_group=None, kernel_fn: Optional[Callable] = None, use_fused_encoding: bool = True):
         self.model = model
         self.group = process_group
         self.distributed = dist.is_available() and dist.is_initialized()
@@ -85,6 +85,15 @@ class DataParallelTrainer:
         if self.distributed:                               # replicas must start identical
             for p in model.parameters():
                 dist.broadcast(p.data, src=0, group=process_group)
+        # whole-model fused kernel (frequency layers evaluated in-kernel, x / grad_x never materialised):
+        # needs the register tier with one thread per sample and the standard n-angles-per-block layout
+        self.kernel_events = None      # set to a list to collect (start, end) CUDA events around the kernel call
+        self.fused_encoding = False
+        if kernel_fn is None and use_fused_encoding and p0.is_cuda:
+            from .ops import encoded_supported
+            q = model.quantum_layer
+            standard = all(e == q.n_wires and d >= 1 for e, d in q.block_configs)
+            self.fused_encoding = standard and encoded_supported(q.n_wires, p0.dtype)
 
     # -- one step -------------------------------------------------------------------------------
     @torch.no_grad()
@@ -96,6 +105,8 @@ class DataParallelTrainer:
         B = y.shape[0]
         gB = global_batch if global_batch is not None else B * self.world_size
         scale = 2.0 / gB
+        if self.fused_encoding:
+            return self._compute_grads_fused(inputs, y, scale, gB)
         if self.is_onet:
             branch, trunk = inputs
             x = torch.cat([m.trunk_freq(trunk), m.branch_freq(branch)], dim=1)
@@ -108,7 +119,9 @@ class DataParallelTrainer:
                                       "(n encoding angles per block) in the fused training step")
         need_gx = bool(m.if_trainable_freq)
         bias = m.bias if hasattr(m, "bias") else None
+        ev = self._event_start()
         out, g, gx, gw = self.kernel_fn(xc, q.ansatz_weights, y.reshape(-1), bias, scale, q, depths, need_gx)
+        self._event_end(ev)
         self.flat_grad.zero_()
         q.ansatz_weights.grad.copy_(gw)
         if bias is not None:
@@ -125,6 +138,66 @@ class DataParallelTrainer:
                 m.freq.weights.grad.copy_(gw_f)
                 m.freq.bias.grad.copy_(gb_f)
         self.flat_grad[-1] = (g * g).sum() / (scale * scale)          # sum of squared residuals on this shard
+        if self.distributed and self.world_size > 1:
+            dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM, group=self.group)
+        return self.flat_grad[-1] / gB
+
+    def _event_start(self):
+        if self.kernel_events is None:
+            return None
+        e0 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        return e0
+
+    def _event_end(self, e0):
+        if e0 is not None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            self.kernel_events.append((e0, e1))
+
+    def _freq_vectors(self):
+        """(fw, fb) over all encoding columns in circuit order (trunk first, core/models_pt.py:163-164)."""
+        m = self.model
+        layers = (m.trunk_freq, m.branch_freq) if self.is_onet else (m.freq,)
+        if m.if_trainable_freq:
+            return torch.cat([l.weights for l in layers]), torch.cat([l.bias for l in layers])
+        p0 = self.params[0]
+        fw = torch.cat([torch.full((l.out_features,), float(l.scale), dtype=p0.dtype, device=p0.device) for l in layers])
+        return fw, None
+
+    def _compute_grads_fused(self, inputs, y, scale, gB):
+        from .ops import encoded_mse_step
+        m = self.model
+        q = m.quantum_layer
+        depths = [d for _, d in q.block_configs]
+        fw, fb = self._freq_vectors()
+        if self.is_onet:
+            branch, trunk = inputs
+            u0, u1, K0 = trunk, branch, m.trunk_enc_size // q.n_wires
+        else:
+            (u1,) = inputs
+            u0, K0 = None, 0
+        bias = m.bias if hasattr(m, "bias") else None
+        tf = bool(m.if_trainable_freq)
+        if q.use_full_ham:
+            ham = (q.ham_diag.to(device=u1.device, dtype=fw.dtype), _DIAG_ORDER[q.diag_order], 0.0, 0.0, _lib.QON_HAM_DIAG)
+        else:
+            ham = (None, _lib.QON_DIAG_LSB0, q.ham_offset, q.ham_coeff, _PAULI_KIND[q.ham_pauli])
+        ev = self._event_start()
+        gw, gfw, gfb, sums = encoded_mse_step(u0, u1, fw, fb, K0, q.ansatz_weights, y.reshape(-1), bias, scale,
+                                              q.n_wires, depths, *ham, tf)
+        self._event_end(ev)
+        self.flat_grad.zero_()
+        q.ansatz_weights.grad.copy_(gw)
+        if bias is not None:
+            m.bias.grad.copy_(sums[0:1])
+        if tf:
+            off = 0
+            for layer in ((m.trunk_freq, m.branch_freq) if self.is_onet else (m.freq,)):
+                layer.weights.grad.copy_(gfw[off:off + layer.out_features])
+                layer.bias.grad.copy_(gfb[off:off + layer.out_features])
+                off += layer.out_features
+        self.flat_grad[-1] = sums[1]
         if self.distributed and self.world_size > 1:
             dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM, group=self.group)
         return self.flat_grad[-1] / gB

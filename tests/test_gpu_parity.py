@@ -257,3 +257,59 @@ def test_larger_qubit_counts(cuda_device, n):
         o, gx, gw = hea_expval_backward(t(g), t(x), t(w), n, depths, None, 0, off, co, 0, True)
         errs = (rel_l2(o[:, 0].cpu().numpy(), e), rel_l2(gx.cpu().numpy(), egx), rel_l2(gw.cpu().numpy(), egw))
         assert max(errs) < tol, (n, dtype, plan_tier(B, n, dtype), errs)
+
+
+@pytest.mark.parametrize("tf", [True, False])
+@pytest.mark.parametrize("kind", ["quanonet", "heaqnn"])
+def test_fused_encoding_matches_unfused(cuda_device, tf, kind):
+    """qon_encoded_forward / qon_encoded_mse_step (frequency layers inside the kernel) against the unfused
+    path (torch frequency layers + qon_hea_mse_forward_backward) and the fp64 oracle-backed autograd."""
+    from quanonet_b200.core.models_pt import HEAQNNPT, QuanONetPT
+    from quanonet_b200.train import DataParallelTrainer
+    dev = cuda_device
+    for dtype, tol in ((torch.float32, 2e-5), (torch.float64, 1e-10)):
+        n = 5 if dtype == torch.float32 else 4
+        torch.manual_seed(11)
+        if kind == "quanonet":
+            mk = lambda: QuanONetPT(n, 7, 2, (3, 2, 2, 1), scale_coeff=0.3, if_trainable_freq=tf, ham_bound=(-2.0, 4.0))
+            B = 77
+            inputs = (torch.randn(B, 7), torch.rand(B, 2))
+        else:
+            mk = lambda: HEAQNNPT(n, 6, (4, 2, 0, 0), scale_coeff=0.4, if_trainable_freq=tf)
+            B = 45
+            inputs = (torch.randn(B, 6),)
+        y = torch.randn(B, 1)
+        ma = mk().to(device=dev, dtype=dtype)
+        if tf:
+            with torch.no_grad():
+                for mod in ma.modules():
+                    if hasattr(mod, "weights") and hasattr(mod, "out_features"):
+                        mod.weights.uniform_(-0.5, 0.5)
+                        mod.bias.uniform_(-3, 3)
+        mb = mk().to(device=dev, dtype=dtype)
+        mb.load_state_dict(ma.state_dict())
+        ins = tuple(t.to(device=dev, dtype=dtype) for t in inputs)
+        yd = y.to(device=dev, dtype=dtype)
+        ta = DataParallelTrainer(ma, lr=1e-2, optimizer="sgd", use_fused_encoding=True)
+        tb = DataParallelTrainer(mb, lr=1e-2, optimizer="sgd", use_fused_encoding=False)
+        assert ta.fused_encoding and not tb.fused_encoding
+        la = ta.compute_grads(ins, yd)
+        lb = tb.compute_grads(ins, yd)
+        assert abs(float(la) - float(lb)) <= tol * abs(float(lb))
+        assert rel_l2(ta.flat_grad.cpu().numpy(), tb.flat_grad.cpu().numpy()) < tol
+        # fused inference path (no_grad) == module forward under autograd
+        with torch.no_grad():
+            fused = ma(*ins)
+        with torch.enable_grad():
+            plain = ma(*ins)
+        assert rel_l2(fused.cpu().numpy(), plain.detach().cpu().numpy()) < tol
+        # and autograd of the unfused module gives the same gradients as the fused step
+        mb.zero_grad()
+        for p_ in mb.parameters():
+            p_.grad = None
+        loss = torch.nn.functional.mse_loss(mb(*ins), yd)
+        loss.backward()
+        got = {k: p.grad.clone() for k, p in ma.named_parameters()}
+        for k, p in mb.named_parameters():
+            if p.grad is not None and float(p.grad.abs().max()) > 0:
+                assert rel_l2(got[k].cpu().numpy(), p.grad.cpu().numpy()) < tol, (k, dtype)
