@@ -340,7 +340,7 @@ def run_b200(args):
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "num_qubits": N_QUBITS, "net_size": list(NET),
                        "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world}",
-                       "l2_policy": "inputs larger than L2: per-step inputs 412 MB + 1.2 GB encoding matrix vs 126 MB L2",
+                       "l2_policy": "inputs larger than L2: 412 MB of (branch, trunk, target) per step vs 126 MB L2",
                        "step": ("ONE kernel: frequency layers + forward + MSE + adjoint-grad + batch reduction of all "
                                 "2,401 gradients; then all-reduce + Adam" if trainer.fused_encoding else
                                 "freq layers (torch) + fused fwd/MSE/adjoint-grad kernel + chain rule (torch) + "

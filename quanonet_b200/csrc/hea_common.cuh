@@ -96,6 +96,17 @@ __device__ __forceinline__ void sincos_half(float t, float& s, float& c) {
 }
 __device__ __forceinline__ void sincos_half(double t, double& s, double& c) { sincos(0.5 * t, &s, &c); }
 
+// geometry of the fp32 shared-memory tier (hea_smem.cuh)
+constexpr int kSmemMinN = 6, kSmemMaxN = 13, kSmemW = 5, kSmemMaxP = 3;
+struct SmemGeom {
+    int n, P;
+    int lo[kSmemMaxP], gm[kSmemMaxP];
+    int tps_log2;      // log2(threads per sample) = n - 5
+    int spc;           // samples per CTA = THREADS >> tps_log2
+    int region_bytes;  // 8 << n
+    int vp;            // moment slots per sublayer in a partial row (>= 3n)
+};
+
 __device__ __forceinline__ Vec4<float> ldg4(const Vec4<float>* p) {
     const float4 v = __ldg(reinterpret_cast<const float4*>(p));
     return Vec4<float>{v.x, v.y, v.z, v.w};

@@ -31,4 +31,14 @@ cudaError_t generic_launch_f32(int n, int mode, int grid, const GenericPlan& gp,
 cudaError_t generic_launch_f64(int n, int mode, int grid, const GenericPlan& gp, const HeaParams<double>& p, int vp,
                                double* gstate, cudaStream_t st);
 
+// fp32 shared-memory tier (hea_smem.cu): n in [kSmemMinN, kSmemMaxN], modes 0 / 1 / 2
+struct SmemPlan {
+    bool ok;
+    int threads, blocks_per_sm;
+    size_t smem_bytes;
+    SmemGeom geo;
+};
+SmemPlan smem_plan(int n, int mode);
+cudaError_t smem_launch(int mode, int grid, const SmemPlan& sp, const HeaParams<float>& p, cudaStream_t st);
+
 }  // namespace qon

@@ -4,6 +4,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -224,6 +225,19 @@ RegLaunchInfo reg_info_cached(int dev, int dtype, int nl, int lq, int mode) {
 }
 
 inline size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
+
+// First qubit count served by the fp32 shared-memory tier; below it the lane-distributed register tier
+// is used.  QON_SMEM_FIRST_N overrides the default for experiments (e.g. 11 = lanes up to n = 10).
+// Measured on B200 (profiles/r1_sweep_f32.md): the shared-memory tier beats the lane-distributed register
+// layout at every n >= 6 with gradients (n = 10: 51.9 vs 24.6 TFLOP/s) and ties or wins forward-only.
+int smem_first_n(bool /*grad*/) {
+    static const int v = [] {
+        const char* e = getenv("QON_SMEM_FIRST_N");
+        const int d = e ? atoi(e) : 0;
+        return d > 0 && d < kSmemMinN ? kSmemMinN : d;
+    }();
+    return v > 0 ? v : kSmemMinN;
+}
 inline bool mode_is_grad(int mode) { return mode == 1 || mode == 2 || mode == 4 || mode == 5; }
 inline bool mode_is_enc(int mode) { return mode >= 3; }
 
@@ -232,6 +246,8 @@ struct Plan {
     int nl = 0, lq = 0;
     int grid = 0, rows = 0, vp = 0, fvp = 0, S = 0;
     GenericPlan gp{};
+    SmemPlan sp{};
+    bool fast_smem = false;   // tier 1 served by hea_smem.cuh (fp32) instead of the generic kernel
     size_t off_u = 0, off_r = 0, off_h = 0, off_d = 0, off_i = 0, off_m = 0, off_state = 0, total = 0;
     int64_t rowlen = 0, mpart_len = 0;
 };
@@ -255,7 +271,23 @@ int make_plan(int64_t B, int n, int K, const int* depth, int dtype, int mode, Pl
     const bool grad = mode_is_grad(mode);
     pl->S = (int)S;
     const int max_local = dtype == QON_F32 ? 5 : 4;
-    if (n <= max_local + 5) {
+    pl->fast_smem = false;
+    if (dtype == QON_F32 && !mode_is_enc(mode) && n >= smem_first_n(grad) && n <= kSmemMaxN) {
+        // fp32 shared-memory tier: register-blocked FFMA2 passes over a state held in shared memory
+        pl->sp = smem_plan(n, mode);
+        if (!pl->sp.ok) return fail(QON_ERR_UNSUPPORTED, "shared-memory tier kernel does not fit for n=%d", n);
+        pl->fast_smem = true;
+        pl->tier = 1;
+        const int64_t rounds = (B + pl->sp.geo.spc - 1) / pl->sp.geo.spc;
+        int64_t grid = rounds;
+        const int64_t cap = (int64_t)di.sms * pl->sp.blocks_per_sm;
+        if (grid > cap) grid = cap;
+        if (grid < 1) grid = 1;
+        pl->grid = (int)grid;
+        pl->rows = (int)grid * (pl->sp.threads / 32);
+        pl->vp = pl->sp.geo.vp;
+        pl->fvp = 0;
+    } else if (n <= max_local + 5) {
         pl->tier = 0;
         pl->nl = n <= max_local ? n : max_local;
         pl->lq = n - pl->nl;
@@ -398,6 +430,9 @@ int run(const Job& j) {
         if (pl.tier == 0) {
             if constexpr (sizeof(T) == 4) e = reg_launch_f32(pl.nl, pl.lq, mode, pl.grid, (const HeaParams<float>&)p, st);
             else e = reg_launch_f64(pl.nl, pl.lq, mode, pl.grid, (const HeaParams<double>&)p, st);
+        } else if (pl.fast_smem) {
+            if constexpr (sizeof(T) == 4) e = smem_launch(mode, pl.grid, pl.sp, (const HeaParams<float>&)p, st);
+            else e = cudaErrorInvalidValue;
         } else {
             T* gstate = pl.tier == 2 ? (T*)(base + pl.off_state) : nullptr;
             if constexpr (sizeof(T) == 4)

@@ -313,3 +313,83 @@ def test_fused_encoding_matches_unfused(cuda_device, tf, kind):
         for k, p in mb.named_parameters():
             if p.grad is not None and float(p.grad.abs().max()) > 0:
                 assert rel_l2(got[k].cpu().numpy(), p.grad.cpu().numpy()) < tol, (k, dtype)
+
+
+def test_infer_api_and_solver_training(cuda_device, tmp_path):
+    """load_model / predict / evaluate on the shipped Antideriv weights (saved here as a MindSpore-named
+    .npz inside a reference-style experiment directory) and a short B200Solver training run."""
+    from quanonet_b200 import infer
+    from quanonet_b200.solvers.solver_pt import B200Solver
+    z = np.load(os.path.join(GOLDEN, "pretrained.npz"))
+    d = tmp_path / "Antideriv_QuanONet_Net5-1-5-1_Q2_TF_S0.001_1000x100_Seed0"
+    d.mkdir()
+    np.savez(d / "best_model.npz", **{
+        "bias": z["Antideriv/bias"][0], "QuanONet.weight": z["Antideriv/quantum_layer.ansatz_weights"].reshape(-1),
+        "branch_LinearLayer.Net2.weights": z["Antideriv/branch_freq.weights"],
+        "branch_LinearLayer.Net2.bias": z["Antideriv/branch_freq.bias"],
+        "trunk_LinearLayer.Net2.weights": z["Antideriv/trunk_freq.weights"],
+        "trunk_LinearLayer.Net2.bias": z["Antideriv/trunk_freq.bias"]})
+    model, cfg = infer.load_model(str(d / "best_model.npz"), branch_in=10, trunk_in=1, device="cuda:0")
+    assert cfg["num_qubits"] == 2 and cfg["net_size"] == (5, 1, 5, 1)
+    cf = np.load(os.path.join(GOLDEN, "antideriv_closed_form.npz"))
+    pred = infer.predict(model, cf["cos/branch"], cf["cos/trunk"], cfg, batch_size=37)
+    assert pred.shape == (100, 1)
+    m = infer.evaluate(pred, cf["cos/truth"])
+    assert abs(m["rel_l2"] - 0.026915) < 2e-5 and abs(m["mse"] - 3.6332e-05) < 1e-8
+    # short training run on the antiderivative of random cubics: loss must drop
+    rng = np.random.default_rng(0)
+    xs = np.linspace(0, 1, 10)
+    coef = rng.uniform(-1, 1, (256, 3))
+    branch = coef[:, :1] + coef[:, 1:2] * xs + coef[:, 2:3] * xs ** 2
+    t = rng.random((256, 1))
+    y = coef[:, :1] * t + coef[:, 1:2] * t ** 2 / 2 + coef[:, 2:3] * t ** 3 / 3
+    data = {"train_branch_input": branch, "train_trunk_input": t, "train_output": y,
+            "test_branch_input": branch[:64], "test_trunk_input": t[:64], "test_output": y[:64]}
+    cfgt = {"model_type": "QuanONet", "num_qubits": 3, "net_size": [3, 1, 3, 1], "scale_coeff": 0.5,
+            "if_trainable_freq": "true", "learning_rate": 0.02, "num_epochs": 30, "batch_size": 64, "ham_bound": [-2, 2],
+            "output_dir": str(tmp_path / "run"), "seed": 1}
+    torch.manual_seed(0)
+    s = B200Solver(cfgt, data, device="cuda:0")
+    hist = s.train()
+    assert hist["loss_train"][-1] < 0.5 * hist["loss_train"][0]
+    met = s.evaluate()
+    assert np.isfinite(met["rel_l2"]) and os.path.exists(tmp_path / "run" / "best_model.npz")
+    # the written checkpoint loads back through the inference API (PyTorch-named npz)
+    m2, _ = infer.load_model(str(tmp_path / "run" / "best_model.npz"), branch_in=10, trunk_in=1, device="cuda:0",
+                             model_type="QuanONet", net_size=(3, 1, 3, 1), num_qubits=3, scale_coeff=0.5,
+                             ham_bound=(-2, 2))
+    with torch.no_grad():
+        a = m2(s.test_in[0], s.test_in[1])
+        b = s.model(s.test_in[0], s.test_in[1])
+    assert torch.allclose(a, b, atol=1e-6)
+
+
+def test_lane_distributed_register_tier_fp32(cuda_device):
+    """fp32 at n = 6..10 defaults to the shared-memory tier; the lane-distributed register layout
+    (2^LQ lanes per sample, __shfl_xor gates) is still built and must agree with the oracle.  Run in a
+    subprocess because the tier override is read once per process."""
+    import subprocess
+    import sys
+    code = r'''
+import sys, numpy as np, torch
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+from oracle import hea_oracle as orc
+from quanonet_b200.ops import hea_expval_backward, plan_tier
+from helpers import rel_l2
+for n in (6, 9, 10):
+    assert plan_tier(8, n, torch.float32) == (0, n - 5), plan_tier(8, n, torch.float32)
+    rng = np.random.default_rng(n)
+    blocks = orc.make_block_configs(n, 2, 1, 1, 2); depths = [d for _, d in blocks]
+    x = rng.uniform(-3, 3, (7, n * 3)).astype(np.float32); w = rng.uniform(-3, 3, (4, 3, n)).astype(np.float32)
+    g = rng.standard_normal(7).astype(np.float32)
+    e, egx, egw = orc.hea_forward_backward(x, w, n, blocks, orc.ham_from_bound(n), grad_out=g)
+    t = lambda a: torch.tensor(a, device="cuda:0")
+    off, co = orc.ham_params(n)
+    o, gx, gw = hea_expval_backward(t(g), t(x), t(w), n, depths, None, 0, off, co, 0, True)
+    errs = (rel_l2(o[:, 0].cpu().numpy(), e), rel_l2(gx.cpu().numpy(), egx), rel_l2(gw.cpu().numpy(), egw))
+    assert max(errs) < 1e-5, (n, errs)
+print("LANES_OK")
+''' % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, QON_SMEM_FIRST_N="14")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=600)
+    assert "LANES_OK" in r.stdout, r.stdout + r.stderr
