@@ -41,4 +41,18 @@ struct SmemPlan {
 SmemPlan smem_plan(int n, int mode);
 cudaError_t smem_launch(int mode, int grid, const SmemPlan& sp, const HeaParams<float>& p, cudaStream_t st);
 
+// fp32 HBM-streamed tier (hea_hbm.cu): n in [kHbmMinN, kHbmMaxN], modes 0 / 1 / 2
+constexpr int kHbmMinN = 14, kHbmMaxN = 22;
+struct HbmPlan {
+    bool ok;
+    int n, tiles_log2;
+    int64_t Sc;                    // samples resident in the HBM workspace per chunk
+    int grid_fwd, grid_rev, rows;  // persistent grids; rows = per-warp partial rows the reverse kernels write
+    size_t smem_fwd, smem_rev;
+    size_t off_psi, off_lam, off_epart, off_gval, off_mx, bytes;   // layout of the state area
+};
+HbmPlan hbm_plan(int64_t B, int n, int K, int mode);
+cudaError_t hbm_run(const HeaParams<float>& p, const int* depth_host, int n, int K, int mode, const HbmPlan& pl,
+                    char* state_ws, cudaStream_t st);
+
 }  // namespace qon

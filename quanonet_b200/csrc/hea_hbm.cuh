@@ -1,0 +1,331 @@
+// HBM-streamed tier (fp32, n = 14 ... 22): the states of a chunk of samples live in the HBM workspace and
+// are streamed through shared memory in TILES of 2^13 amplitudes (64 KB of psi, + 64 KB of lam in the
+// reverse sweep).  One ansatz sublayer = TWO passes over HBM, each a kernel launch over all tiles of the chunk:
+//
+//   pass A  tile = 2^13 contiguous amplitudes          -> gates on qubits 0..12   (windows [0,5) [5,10) [8,13))
+//   pass B  tile = 2^c-amplitude contiguous chunks x the n-13 high qubits (c = 26-n)
+//                                                      -> gates on qubits 13..n-1, then the CNOT ring as a
+//                                                         GF(2)-linear scatter on the way back to HBM
+//
+// Inside a tile the register-blocked FFMA2 window passes of the shared-memory tier (hea_smem.cuh) are reused
+// unchanged (same swizzle, same constant-memory offset tables, n = 13 geometry); windows always run five
+// gates and take identity coefficients for bits that carry no gate in this pass (pass B is HBM-bound, so
+// the padding is free; pass A wastes 2 of 15).  Algorithmic HBM traffic: 2 x (read + write) x 8 B x 2^n per
+// sublayer forward, 2 x that in the reverse sweep (psi and lam); the encoding layers cost none (RX folded).
+//
+// The reverse sweep runs the same two passes backwards on (psi, lam): pass B first (gathers through the
+// ring permutation), then pass A; shared-parameter moments go to the per-warp rows as in the other tiers,
+// per-sample dL/dx moments go to a per-(sample, tile) partial buffer summed in fixed order afterwards.
+// Reference semantics: core/quantum_circuits_tq.py:65-127.
+#pragma once
+#include "hea_smem.cuh"
+
+namespace qon {
+
+constexpr int kTileBits = 13;
+constexpr int kTileAmps = 1 << kTileBits;
+constexpr int kHbmThreads = 256;
+
+struct HbmPass {
+    int n, c;                     // c = contiguous low bits of a tile chunk (13 for pass A, 26 - n for pass B)
+    int nwin;                     // windows to run, in execution order
+    int win[3], mask[3];          // window index into the n = 13 tables (lo = 0, 5, 8) and its gate mask
+    int qoff;                     // qubit of local bit l (for gated bits) = l + qoff
+    int s, kblk, fold;            // sublayer, block (x columns kblk*n ..), RX folded into this sublayer
+    int reverse;                  // 0 forward (psi only), 1 reverse (psi and lam, moments)
+    int ring_store, ring_load;    // scatter / gather through the CNOT-ring permutation
+    int scale_lam;                // multiply lam by g[sample] while loading (first reverse pass)
+    int tiles_log2;               // log2(tiles per sample) = n - 13
+    int need_gx;
+    int64_t b0, nb;               // first sample of the chunk, samples in the chunk
+    unsigned ringp[kTileBits];    // ring(gidx(e_l)) for the 13 local bits
+};
+
+struct HbmBuffers {
+    u64* psi;          // [Sc][2^n]
+    u64* lam;          // [Sc][2^n]            (reverse only)
+    float* epart;      // [Sc][T]
+    float* gval;       // [Sc]                 upstream gradient per sample
+    float* mxpart;     // [Sc][T][3*n*K]       per-tile Pauli moments of the folded RX gates
+};
+
+__device__ __forceinline__ void cp_async8(unsigned smem_addr, const void* gptr) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(smem_addr), "l"(gptr) : "memory");
+}
+
+// window group <-> shared-memory tile; the tile base is ADDED (not XORed as in hea_smem.cuh) so the tile
+// needs no size alignment and two forward CTAs fit in one SM's shared memory
+__device__ __forceinline__ void tile_load(SmemState& st, unsigned region, unsigned gb, const int* off) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) st.a[i] = lds64(region + (gb ^ (unsigned)off[i]));
+}
+__device__ __forceinline__ void tile_store(const SmemState& st, unsigned region, unsigned gb, const int* off) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) sts64(region + (gb ^ (unsigned)off[i]), st.a[i]);
+}
+
+__device__ __forceinline__ unsigned hbm_ring(unsigned k, int n) {
+    for (int i = 0; i < n; ++i) k ^= ((k >> (i + 1 == n ? 0 : i + 1)) & 1u) << i;
+    return k;
+}
+// global amplitude index of local index l in tile t
+__device__ __forceinline__ unsigned hbm_gidx(unsigned l, unsigned t, int c) {
+    return (l & ((1u << c) - 1u)) | (t << c) | ((l >> c) << kTileBits);
+}
+
+template <bool REVERSE>
+__global__ void __launch_bounds__(kHbmThreads, REVERSE ? 1 : 2) hea_hbm_pass_kernel(const HeaParams<float> p, const HbmPass hp,
+                                                                      const HbmBuffers hb) {
+    using State = SmemState;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ float s_red[kHbmThreads / 32][16];
+    constexpr int WARPS = kHbmThreads / 32;
+    const int n = hp.n, c = hp.c;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned raw = (unsigned)__cvta_generic_to_shared(smem_raw);
+    const unsigned rb = 8u << kTileBits;
+    const unsigned psi_base = raw;   // addresses are base + (group ^ offset): no alignment slack, 2 forward CTAs per SM
+    const unsigned lam_base = psi_base + rb;
+    const int VP = (3 * n + 3) / 4 * 4;
+    const int64_t gwarp = (int64_t)blockIdx.x * WARPS + warp;
+    float* mrow = REVERSE ? p.mpart + gwarp * p.rowlen : nullptr;
+    const int64_t T = (int64_t)1 << hp.tiles_log2;
+    const int64_t ntiles = hp.nb * T;
+    const int64_t N = (int64_t)1 << n;
+
+    auto group_base = [&](int lo) -> unsigned {
+        const int kb = ((tid >> lo) << (lo + kSmemW)) | (tid & ((1 << lo) - 1));
+        return (unsigned)(8 * smem_swz(kb));
+    };
+
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int64_t sl = tile >> hp.tiles_log2;            // sample slot in the chunk
+        const unsigned t = (unsigned)(tile & (T - 1));
+        const int64_t b = hp.b0 + sl;
+        const u64* gpsi = hb.psi + sl * N;
+        u64* gpsi_w = hb.psi + sl * N;
+        const u64* glam = REVERSE ? hb.lam + sl * N : nullptr;
+        u64* glam_w = REVERSE ? hb.lam + sl * N : nullptr;
+        // lam is carried UNSCALED (= H psi) through the reverse sweep; the upstream gradient g of this tile's
+        // sample multiplies the moments where they are consumed (they are linear in lam)
+        const float gsample = REVERSE ? hb.gval[sl] : 1.f;
+
+        // ---------------- HBM -> shared memory: cp.async straight into the swizzled slots (no register
+        // staging, all 32 (64) copies of a thread in flight at once); gather through the ring when asked ------
+        {
+            // ring(gidx(l)) is GF(2)-linear in l = tid + 256 r: thread part once per tile, r part = constants
+            unsigned tbase_ring = 0u;
+            if (hp.ring_load) {
+                tbase_ring = hbm_ring(hbm_gidx(0u, t, c), n);
+#pragma unroll
+                for (int bit = 0; bit < 8; ++bit)
+                    if ((tid >> bit) & 1) tbase_ring ^= hp.ringp[bit];
+            }
+#pragma unroll
+            for (int r = 0; r < 32; ++r) {
+                const unsigned l = (unsigned)(tid + 256 * r);      // consecutive lanes -> consecutive amplitudes
+                unsigned src;
+                if (hp.ring_load) {
+                    src = tbase_ring;
+#pragma unroll
+                    for (int bit = 8; bit < kTileBits; ++bit)
+                        if ((r >> (bit - 8)) & 1) src ^= hp.ringp[bit];
+                } else {
+                    src = hbm_gidx(l, t, c);
+                }
+                const unsigned slot = (unsigned)(8 * smem_swz((int)l));
+                cp_async8(psi_base + slot, gpsi + src);
+                if constexpr (REVERSE) cp_async8(lam_base + slot, glam + src);
+            }
+            asm volatile("cp.async.commit_group;\n" ::: "memory");
+            asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+        }
+        __syncthreads();
+
+        // ---------------- window passes on the tile ----------------
+        const float* xk = p.x + b * p.ldx + (int64_t)hp.kblk * n;
+#pragma unroll 1
+        for (int wdx = 0; wdx < hp.nwin; ++wdx) {
+            const int pw = hp.win[wdx], mask = hp.mask[wdx];
+            const int lo = pw == 0 ? 0 : (pw == 1 ? 5 : 8);
+            const unsigned gb = group_base(lo);
+            const int* off = c_smem_tbl.off[kTileBits][pw];
+            State st;
+            tile_load(st, psi_base, gb, off);
+            if constexpr (!REVERSE) {
+                static_for<kSmemW>([&](auto Rc) {
+                    constexpr int R = decltype(Rc)::value;
+                    const bool gated = (mask >> R) & 1;
+                    const int q = lo + R + hp.qoff;
+                    Vec4<float> u{1.f, 0.f, 0.f, 0.f};
+                    if (gated) u = ldg4(p.ucoef + (int64_t)hp.s * n + q);
+                    float ar = u.x, ai = u.y, br = u.z, bi = u.w;
+                    if (gated && hp.fold) fold_rx_coef(u, __ldg(xk + q), ar, ai, br, bi);
+                    apply_u<R, false>(st, ar, ai, br, bi, lane);
+                });
+                tile_store(st, psi_base, gb, off);
+            } else {
+                State lm;
+                tile_load(lm, lam_base, gb, off);
+                float mv[15];
+                static_for<kSmemW>([&](auto Rc) {
+                    constexpr int R = kSmemW - 1 - decltype(Rc)::value;
+                    const bool gated = (mask >> R) & 1;
+                    const int q = lo + R + hp.qoff;
+                    Vec4<float> u{1.f, 0.f, 0.f, 0.f};
+                    if (gated) u = ldg4(p.ucoef + (int64_t)hp.s * n + q);
+                    float ar = u.x, ai = u.y, br = u.z, bi = u.w;
+                    if (gated && hp.fold) fold_rx_coef(u, __ldg(xk + q), ar, ai, br, bi);
+                    bwd_group<R>(st, lm, ar, ai, br, bi, lane, mv[3 * R], mv[3 * R + 1], mv[3 * R + 2]);
+                });
+                tile_store(st, psi_base, gb, off);
+                tile_store(lm, lam_base, gb, off);
+                // shared-parameter moments -> this warp's partial row; keep warp totals for the per-tile dL/dx part
+                float bv[16];
+#pragma unroll
+                for (int i = 0; i < 15; ++i) bv[i] = mv[i];
+                bv[15] = 0.f;
+                const float tot = gsample * butterfly_reduce<float, 16>(bv, lane);
+                const int slot = lane >> 1, R = slot / 3;
+                const bool mine = (lane & 1) == 0 && slot < 15 && ((mask >> R) & 1);
+                if (mine) atomicAdd(mrow + (int64_t)hp.s * VP + 3 * (lo + R + hp.qoff) + slot % 3, tot);
+                if (hp.fold && hp.need_gx) {
+                    if ((lane & 1) == 0 && slot < 15) s_red[warp][slot] = tot;
+                    __syncthreads();
+                    if (tid < 15 && ((mask >> (tid / 3)) & 1)) {
+                        float acc = 0.f;
+                        for (int w = 0; w < WARPS; ++w) acc += s_red[w][tid];
+                        const int q = lo + tid / 3 + hp.qoff;
+                        hb.mxpart[(sl * T + t) * (int64_t)(3 * n * p.K) + ((int64_t)hp.kblk * n + q) * 3 + tid % 3] = acc;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+
+        // ---------------- shared memory -> HBM (scatter through the ring when asked) ----------------
+        {
+            unsigned tbase_ring = 0u;
+            if (hp.ring_store) {
+                tbase_ring = hbm_ring(hbm_gidx(0u, t, c), n);
+#pragma unroll
+                for (int bit = 0; bit < 8; ++bit)
+                    if ((tid >> bit) & 1) tbase_ring ^= hp.ringp[bit];
+            }
+#pragma unroll 8
+            for (int r = 0; r < 32; ++r) {
+                {
+                    const unsigned l = (unsigned)(tid + 256 * r);
+                    unsigned dst;
+                    if (hp.ring_store) {
+                        dst = tbase_ring;
+#pragma unroll
+                        for (int bit = 8; bit < kTileBits; ++bit)
+                            if ((r >> (bit - 8)) & 1) dst ^= hp.ringp[bit];
+                    } else {
+                        dst = hbm_gidx(l, t, c);
+                    }
+                    const unsigned slot = (unsigned)(8 * smem_swz((int)l));
+                    gpsi_w[dst] = lds64(psi_base + slot);
+                    if constexpr (REVERSE) glam_w[dst] = lds64(lam_base + slot);
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// |0...0> for every sample slot of the chunk
+__global__ void hea_hbm_init_kernel(u64* psi, int64_t N, int64_t nb) {
+    const int64_t total = N * nb;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x)
+        psi[i] = (i % N) == 0 ? pack2(1.f, 0.f) : 0ull;
+}
+
+// E partials per (sample, tile of 8192 contiguous amplitudes); lam = H psi for the reverse sweep
+template <bool GRAD>
+__global__ void __launch_bounds__(256) hea_hbm_measure_kernel(const HeaParams<float> p, int n, int tiles_log2, int64_t nb,
+                                                              const HbmBuffers hb) {
+    __shared__ float red[8];
+    const int64_t T = (int64_t)1 << tiles_log2, N = (int64_t)1 << n;
+    for (int64_t tile = blockIdx.x; tile < nb * T; tile += gridDim.x) {
+        const int64_t sl = tile >> tiles_log2, t = tile & (T - 1);
+        const u64* ps = hb.psi + sl * N;
+        float e = 0.f;
+        for (int i = threadIdx.x; i < kTileAmps; i += blockDim.x) {
+            const int64_t k = t * kTileAmps + i;
+            const u64 v = ps[k];
+            u64 h;
+            if (p.pauli == 0) {
+                h = mul2<0>(__ldg(p.hdiag + k), v);
+            } else {
+                h = mul2<0>(p.offset, v);
+                for (int q = 0; q < n; ++q) {
+                    const u64 f = ps[k ^ ((int64_t)1 << q)];
+                    if (p.pauli == 1) h = fma2<0>(p.coeff, f, h);
+                    else h = fma2<2>(((k >> q) & 1) ? p.coeff : -p.coeff, f, h);
+                }
+            }
+            float vr, vi, hr, hi;
+            unpack2(v, vr, vi);
+            unpack2(h, hr, hi);
+            e = fmaf(vr, hr, e);
+            e = fmaf(vi, hi, e);
+            if constexpr (GRAD) hb.lam[sl * N + k] = h;
+        }
+#pragma unroll
+        for (int m = 16; m >= 1; m >>= 1) e += __shfl_xor_sync(0xffffffffu, e, m);
+        __syncthreads();
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = e;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float s = 0.f;
+            for (int w = 0; w < 8; ++w) s += red[w];
+            hb.epart[sl * T + t] = s;
+        }
+    }
+}
+
+// per sample: E = sum of tile partials (fixed order), out, upstream gradient g
+__global__ void hea_hbm_seed_kernel(const HeaParams<float> p, int tiles_log2, int64_t b0, int64_t nb, const HbmBuffers hb,
+                                    int grad) {
+    const int64_t T = (int64_t)1 << tiles_log2;
+    for (int64_t sl = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; sl < nb; sl += (int64_t)gridDim.x * blockDim.x) {
+        float e = 0.f;
+        for (int64_t t = 0; t < T; ++t) e += hb.epart[sl * T + t];
+        const int64_t b = b0 + sl;
+        p.out[b] = e;
+        if (grad) {
+            float g;
+            if (p.target) {
+                g = p.gscale * (e + (p.bias ? p.bias[0] : 0.f) - p.target[b]);
+                if (p.gbuf) p.gbuf[b] = g;
+            } else {
+                g = p.gout[b];
+            }
+            hb.gval[sl] = g;
+        }
+    }
+}
+
+// dL/dx[b, col] = r(col) . sum over tiles of the per-tile moments (fixed order)
+__global__ void hea_hbm_gx_kernel(const HeaParams<float> p, int n, int tiles_log2, int64_t b0, int64_t nb,
+                                  const HbmBuffers hb) {
+    const int64_t T = (int64_t)1 << tiles_log2;
+    const int64_t cols = (int64_t)n * p.K;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nb * cols; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t sl = i / cols, col = i % cols;
+        float m[3] = {0.f, 0.f, 0.f};
+        for (int64_t t = 0; t < T; ++t) {
+            const float* src = hb.mxpart + (sl * T + t) * (3 * cols) + col * 3;
+            m[0] += src[0]; m[1] += src[1]; m[2] += src[2];
+        }
+        const int k = (int)(col / n), q = (int)(col % n);
+        int s0 = 0;                                       // first sublayer of block k
+        for (int kk = 0; kk < k; ++kk) s0 += p.depth[kk];
+        const Vec4<float> rc = ldg4(p.rcoef + (int64_t)s0 * n + q);
+        p.gx[(b0 + sl) * p.ldgx + col] = fmaf(rc.z, m[2], fmaf(rc.y, m[1], rc.x * m[0]));
+    }
+}
+
+}  // namespace qon

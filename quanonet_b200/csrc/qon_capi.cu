@@ -228,6 +228,15 @@ inline size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
 
 // First qubit count served by the fp32 shared-memory tier; below it the lane-distributed register tier
 // is used.  QON_SMEM_FIRST_N overrides the default for experiments (e.g. 11 = lanes up to n = 10).
+// QON_HBM_TIER=generic falls back to the one-CTA-per-sample kernel for n >= 14 (experiments / A-B tests)
+bool hbm_disabled() {
+    static const bool v = [] {
+        const char* e = getenv("QON_HBM_TIER");
+        return e && strcmp(e, "generic") == 0;
+    }();
+    return v;
+}
+
 // Measured on B200 (profiles/r1_sweep_f32.md): the shared-memory tier beats the lane-distributed register
 // layout at every n >= 6 with gradients (n = 10: 51.9 vs 24.6 TFLOP/s) and ties or wins forward-only.
 int smem_first_n(bool /*grad*/) {
@@ -248,6 +257,8 @@ struct Plan {
     GenericPlan gp{};
     SmemPlan sp{};
     bool fast_smem = false;   // tier 1 served by hea_smem.cuh (fp32) instead of the generic kernel
+    HbmPlan hp{};
+    bool fast_hbm = false;    // tier 2 served by hea_hbm.cuh (fp32) instead of the generic kernel
     size_t off_u = 0, off_r = 0, off_h = 0, off_d = 0, off_i = 0, off_m = 0, off_state = 0, total = 0;
     int64_t rowlen = 0, mpart_len = 0;
 };
@@ -272,6 +283,7 @@ int make_plan(int64_t B, int n, int K, const int* depth, int dtype, int mode, Pl
     pl->S = (int)S;
     const int max_local = dtype == QON_F32 ? 5 : 4;
     pl->fast_smem = false;
+    pl->fast_hbm = false;
     if (dtype == QON_F32 && !mode_is_enc(mode) && n >= smem_first_n(grad) && n <= kSmemMaxN) {
         // fp32 shared-memory tier: register-blocked FFMA2 passes over a state held in shared memory
         pl->sp = smem_plan(n, mode);
@@ -286,6 +298,16 @@ int make_plan(int64_t B, int n, int K, const int* depth, int dtype, int mode, Pl
         pl->grid = (int)grid;
         pl->rows = (int)grid * (pl->sp.threads / 32);
         pl->vp = pl->sp.geo.vp;
+        pl->fvp = 0;
+    } else if (dtype == QON_F32 && !mode_is_enc(mode) && n >= kHbmMinN && n <= kHbmMaxN && !hbm_disabled()) {
+        // fp32 HBM-streamed tier: 13-qubit tiles through shared memory, two passes over HBM per sublayer
+        pl->hp = hbm_plan(B, n, K, mode);
+        if (!pl->hp.ok) return fail(QON_ERR_UNSUPPORTED, "HBM-streamed tier kernel does not fit for n=%d", n);
+        pl->fast_hbm = true;
+        pl->tier = 2;
+        pl->grid = pl->hp.grid_rev;
+        pl->rows = pl->hp.rows;
+        pl->vp = (3 * n + 3) / 4 * 4;
         pl->fvp = 0;
     } else if (n <= max_local + 5) {
         pl->tier = 0;
@@ -332,7 +354,8 @@ int make_plan(int64_t B, int n, int K, const int* depth, int dtype, int mode, Pl
     pl->mpart_len = grad ? (int64_t)pl->rows * pl->rowlen : 0;
     off = align_up(off + (size_t)pl->mpart_len * es);
     pl->off_state = off;
-    if (pl->tier == 2) off = align_up(off + (size_t)pl->grid * (grad ? 4 : 2) * ((size_t)1 << n) * es);
+    if (pl->fast_hbm) off = align_up(off + pl->hp.bytes);
+    else if (pl->tier == 2) off = align_up(off + (size_t)pl->grid * (grad ? 4 : 2) * ((size_t)1 << n) * es);
     pl->total = off;
     return 0;
 }
@@ -432,6 +455,10 @@ int run(const Job& j) {
             else e = reg_launch_f64(pl.nl, pl.lq, mode, pl.grid, (const HeaParams<double>&)p, st);
         } else if (pl.fast_smem) {
             if constexpr (sizeof(T) == 4) e = smem_launch(mode, pl.grid, pl.sp, (const HeaParams<float>&)p, st);
+            else e = cudaErrorInvalidValue;
+        } else if (pl.fast_hbm) {
+            if constexpr (sizeof(T) == 4)
+                e = hbm_run((const HeaParams<float>&)p, j.depth, n, K, mode, pl.hp, base + pl.off_state, st);
             else e = cudaErrorInvalidValue;
         } else {
             T* gstate = pl.tier == 2 ? (T*)(base + pl.off_state) : nullptr;

@@ -393,3 +393,33 @@ print("LANES_OK")
     env = dict(os.environ, QON_SMEM_FIRST_N="14")
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=600)
     assert "LANES_OK" in r.stdout, r.stdout + r.stderr
+
+
+@pytest.mark.parametrize("n", [14, 15, 17])
+def test_hbm_streamed_tier(cuda_device, n):
+    """n >= 14: states stream through HBM in 13-qubit tiles (two passes per sublayer, ring as a scatter)."""
+    from oracle import hea_oracle as orc
+    from quanonet_b200.ops import hea_expval, hea_expval_backward, plan_tier
+    assert plan_tier(4, n, torch.float32)[0] == 2
+    rng = np.random.default_rng(n)
+    blocks = orc.make_block_configs(n, 1, 2, 2, 1)
+    depths = [d for _, d in blocks]
+    B = 3
+    x = rng.uniform(-np.pi, np.pi, (B, n * len(blocks))).astype(np.float32)
+    w = rng.uniform(-np.pi, np.pi, (sum(depths), 3, n)).astype(np.float32)
+    g = rng.standard_normal(B).astype(np.float32)
+    e, egx, egw = orc.hea_forward_backward(x, w, n, blocks, orc.ham_from_bound(n), grad_out=g)
+    t = lambda a: torch.tensor(a, device=cuda_device)
+    off, co = orc.ham_params(n)
+    o, gx, gw = hea_expval_backward(t(g), t(x), t(w), n, depths, None, 0, off, co, 0, True)
+    errs = (rel_l2(o[:, 0].cpu().numpy(), e), rel_l2(gx.cpu().numpy(), egx), rel_l2(gw.cpu().numpy(), egw))
+    assert max(errs) < TOL_F32, (n, errs)
+    o2 = hea_expval(t(x), t(w), n, depths, None, 0, off, co, 0)
+    assert rel_l2(o2[:, 0].cpu().numpy(), e) < TOL_F32
+    _, _, gw2 = hea_expval_backward(t(g), t(x), t(w), n, depths, None, 0, off, co, 0, False)
+    assert rel_l2(gw2.cpu().numpy(), egw) < TOL_F32
+    if n == 14:   # Pauli-X observable crosses tiles
+        ex = orc.hea_forward(x, w, n, blocks, orc.ham_from_bound(n, -3, 7, pauli="X"))
+        offx, cox = orc.ham_params(n, -3, 7)
+        ox = hea_expval(t(x), t(w), n, depths, None, 0, offx, cox, 1)
+        assert rel_l2(ox[:, 0].cpu().numpy(), ex) < TOL_F32
