@@ -73,6 +73,8 @@ def _can_fuse_inference(qlayer, u):
         return False
     from ..ops import encoded_supported
     w = qlayer.ansatz_weights
+    if w.dtype == torch.float32 and u.shape[0] <= 2048:
+        return False     # small fp32 batches: the x-given path uses the 2^n-lanes-per-sample latency layout
     return (encoded_supported(qlayer.n_wires, w.dtype)
             and all(e == qlayer.n_wires and d >= 1 for e, d in qlayer.block_configs))
 

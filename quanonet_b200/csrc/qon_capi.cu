@@ -228,6 +228,16 @@ inline size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
 
 // First qubit count served by the fp32 shared-memory tier; below it the lane-distributed register tier
 // is used.  QON_SMEM_FIRST_N overrides the default for experiments (e.g. 11 = lanes up to n = 10).
+// Largest batch served by the one-amplitude-per-lane latency layout (n <= 5, fp32).  Above it the
+// one-thread-per-sample FFMA2 kernel has the higher throughput.  QON_LANES_MAX_B overrides (0 disables).
+int64_t lanes_max_batch() {
+    static const int64_t v = [] {
+        const char* e = getenv("QON_LANES_MAX_B");
+        return e ? (int64_t)atoll(e) : (int64_t)2048;   // measured: 280 us vs 900 us at B <= 1000, break-even ~4096
+    }();
+    return v;
+}
+
 // QON_HBM_TIER=generic falls back to the one-CTA-per-sample kernel for n >= 14 (experiments / A-B tests)
 bool hbm_disabled() {
     static const bool v = [] {
@@ -313,6 +323,11 @@ int make_plan(int64_t B, int n, int K, const int* depth, int dtype, int mode, Pl
         pl->tier = 0;
         pl->nl = n <= max_local ? n : max_local;
         pl->lq = n - pl->nl;
+        // small batches (fp32, n <= 5, x given): one amplitude per lane, 2^n lanes per sample — latency layout
+        if (dtype == QON_F32 && n <= max_local && !mode_is_enc(mode) && B <= lanes_max_batch()) {
+            pl->nl = 0;
+            pl->lq = n;
+        }
         RegLaunchInfo ri = reg_info_cached(dev, dtype, pl->nl, pl->lq, mode);
         if (!ri.ok)
             return fail(QON_ERR_UNSUPPORTED, "register-tier kernel (n=%d, lanes 2^%d, mode %d) is not built%s", n,

@@ -21,3 +21,32 @@ for B in (100, 1000, 10000, 100000):
     for _ in range(20): autograd_step(model, opt, (branch, trunk), y)
     torch.cuda.synchronize(); dta = (time.perf_counter() - t0) / 20
     print(f"B={B:7d}: fused step {dt*1e3:8.3f} ms ({B/dt:.3e} samples/s) | reference-style autograd step {dta*1e3:8.3f} ms ({B/dta:.3e} samples/s)")
+
+# kernel-only latency and CUDA-graph replay of the whole step
+from quanonet_b200.ops import hea_mse_backward
+print("--- kernel only (x given) and graph-replayed training step ---")
+for B in (100, 1000, 4096):
+    model = bench.make_model(dev)
+    tr = DataParallelTrainer(model, lr=1e-3, optimizer_kwargs={'capturable': True})
+    branch, trunk, y = bench.synth_batch(B, 1, device=dev)
+    x = torch.cat([model.trunk_freq(trunk), model.branch_freq(branch)], 1).detach()
+    q = model.quantum_layer; depths = [d for _, d in q.block_configs]
+    f = lambda: hea_mse_backward(x, q.ansatz_weights.detach(), y.reshape(-1), model.bias.detach(), 2.0 / B, 5, depths, None, 0, 0.0, 1.0, 0, True)
+    for _ in range(3): f()
+    torch.cuda.synchronize(); e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+    e0.record()
+    for _ in range(20): f()
+    e1.record(); torch.cuda.synchronize(); kms = e0.elapsed_time(e1) / 20
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        for _ in range(3): tr.step((branch, trunk), y)
+    torch.cuda.current_stream().wait_stream(s)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        tr.step((branch, trunk), y)
+    for _ in range(5): g.replay()
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    for _ in range(200): g.replay()
+    torch.cuda.synchronize(); dt = (time.perf_counter() - t0) / 200
+    print(f"B={B:6d}: op call (prep+kernel+finalize, incl. host) {kms*1e3:7.1f} us | CUDA-graph step {dt*1e6:7.1f} us ({B/dt:.3e} samples/s)")
