@@ -3,10 +3,10 @@ Pauli X/Y/Z sums at n = 5 net (20,2,10,2), ham_bound +-1 ... +-10, explicit diag
 For every case: fp64 CUDA forward + adjoint gradients vs the fp64 oracle on a 48-sample slice (norm-relative error,
 bar 1e-12) and throughput at B samples.
 
-    python scripts/sweep_hamiltonian.py [--batch 262144] [--out profiles/hamiltonian.jsonl]
+    python tests/harness/sweep_hamiltonian.py [--batch 262144] [--out profiles/hamiltonian.jsonl]
 """
 import argparse, json, os, sys, time
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import numpy as np, torch
 from oracle import hea_oracle as orc

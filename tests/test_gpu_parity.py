@@ -507,3 +507,13 @@ def test_solver_cuda_graph_equals_eager(cuda_device):
             for k, v in s.model.state_dict().items():
                 assert torch.allclose(v, params_graph[k], rtol=2e-4, atol=2e-5), k
     assert np.allclose(hist[True], hist[False], rtol=2e-4)
+
+
+def test_compare_backends_harness(cuda_device):
+    """tests/harness/compare_backends_b200.py (the reference's compare_backends.py structure and tolerances)."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tests", "harness", "compare_backends_b200.py")],
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "0 FAIL" in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
