@@ -249,7 +249,7 @@ def test_edge_cases(cuda_device):
         hea_expval(torch.rand(4, 6), w.cpu(), 2, [1, 1, 1], None, 0, 0.0, 2.5, 0)
 
 
-@pytest.mark.parametrize("n", [6, 8, 10, 11, 12])
+@pytest.mark.parametrize("n", [6, 7, 8, 9, 10, 11, 12, 13])
 def test_larger_qubit_counts(cuda_device, n):
     """Lane-distributed register tier (n = 6..10) and the shared-memory tier (n >= 11) vs the oracle."""
     from oracle import hea_oracle as orc
