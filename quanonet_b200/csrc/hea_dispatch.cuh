@@ -45,7 +45,8 @@ cudaError_t smem_launch(int mode, int grid, const SmemPlan& sp, const HeaParams<
 constexpr int kHbmMinN = 14, kHbmMaxN = 22;
 struct HbmPlan {
     bool ok;
-    int n, tiles_log2;
+    int n;
+    int tb_fwd, tb_rev;            // tile size (log2 amplitudes) of the forward / reverse pass kernels: 12 or 13
     int64_t Sc;                    // samples resident in the HBM workspace per chunk
     int grid_fwd, grid_rev, rows;  // persistent grids; rows = per-warp partial rows the reverse kernels write
     size_t smem_fwd, smem_rev;

@@ -1,4 +1,6 @@
 // fp32 HBM-streamed tier: planning and the host-side launch sequence (two tile passes per sublayer).
+#include <cstdlib>
+
 #include "hea_dispatch.cuh"
 #include "hea_hbm.cuh"
 
@@ -7,27 +9,34 @@ namespace qon {
 namespace {
 inline size_t up256(size_t v) { return (v + 255) / 256 * 256; }
 
-unsigned ring_host(unsigned k, int n) {
-    for (int i = 0; i < n; ++i) k ^= ((k >> (i + 1 == n ? 0 : i + 1)) & 1u) << i;
-    return k;
-}
-unsigned gidx_host(unsigned l, unsigned t, int c) {
-    return (l & ((1u << c) - 1u)) | (t << c) | ((l >> c) << kTileBits);
+using PassKern = void (*)(const HeaParams<float>, const HbmPass, const HbmBuffers);
+
+PassKern pass_kernel(bool reverse, int tb) {
+    if (reverse) return tb == 13 ? hea_hbm_pass_kernel<true, 13> : hea_hbm_pass_kernel<true, 12>;
+    return tb == 13 ? hea_hbm_pass_kernel<false, 13> : hea_hbm_pass_kernel<false, 12>;
 }
 
-void make_pass(HbmPass& hp, int n, bool passB, bool reverse) {
+// tile size per direction; QON_HBM_TB_FWD / QON_HBM_TB_REV override (12 or 13) for A/B runs
+int tile_bits(bool reverse) {
+    static const int f = [] { const char* e = getenv("QON_HBM_TB_FWD"); const int v = e ? atoi(e) : 12; return v == 13 ? 13 : 12; }();
+    static const int r = [] { const char* e = getenv("QON_HBM_TB_REV"); const int v = e ? atoi(e) : 12; return v == 13 ? 13 : 12; }();
+    return reverse ? r : f;
+}
+
+void make_pass(HbmPass& hp, int n, int tb, bool passB, bool reverse) {
     hp.n = n;
-    hp.c = passB ? 2 * kTileBits - n : kTileBits;
-    hp.qoff = passB ? kTileBits - hp.c : 0;
+    hp.c = passB ? 2 * tb - n : tb;
+    hp.qoff = passB ? tb - hp.c : 0;
+    const int lo2 = smem_lo(tb, 2);
     int wins[3], masks[3], cnt = 0;
     for (int pw = 0; pw < 3; ++pw) {
-        const int lo = pw == 0 ? 0 : (pw == 1 ? 5 : 8);
+        const int lo = smem_lo(tb, pw);
         int m = 0;
         for (int r = 0; r < 5; ++r) {
             const int l = lo + r;
             bool gated;
-            if (!passB) gated = pw < 2 ? true : l >= 10;                       // pass A: every local bit once
-            else gated = l >= hp.c && (pw == 2 || l < (pw == 1 ? 8 : 5));      // pass B: local bits [c, 13) once
+            if (!passB) gated = pw < 2 ? true : l >= 10;                        // pass A: every local bit once
+            else gated = l >= hp.c && (pw == 2 || l < (pw == 1 ? lo2 : 5));     // pass B: local bits [c, TB) once
             if (gated) m |= 1 << r;
         }
         if (m) { wins[cnt] = pw; masks[cnt] = m; ++cnt; }
@@ -38,7 +47,11 @@ void make_pass(HbmPass& hp, int n, bool passB, bool reverse) {
         hp.win[i] = wins[src];
         hp.mask[i] = masks[src];
     }
-    for (int bit = 0; bit < kTileBits; ++bit) hp.ringp[bit] = ring_host(gidx_host(1u << bit, 0u, hp.c), n);
+    for (int bit = 0; bit < kMaxTileBits; ++bit) {
+        unsigned g = 0;
+        if (bit < tb) g = tb == 13 ? hbm_gidx<13>(1u << bit, 0u, hp.c) : hbm_gidx<12>(1u << bit, 0u, hp.c);
+        hp.ringp[bit] = bit < tb ? hbm_ring(g, n) : 0u;
+    }
 }
 }  // namespace
 
@@ -48,7 +61,8 @@ HbmPlan hbm_plan(int64_t B, int n, int K, int mode) {
     if (n < kHbmMinN || n > kHbmMaxN || mode < 0 || mode > 2) return pl;
     const bool grad = mode != 0;
     pl.n = n;
-    pl.tiles_log2 = n - kTileBits;
+    pl.tb_fwd = tile_bits(false);
+    pl.tb_rev = tile_bits(true);
     const size_t state = (size_t)8 << n;
     // chunk of samples resident in HBM: ~2 GB of state, at least 8 samples, at most B
     int64_t sc = (int64_t)(((size_t)2 << 30) / (state * (grad ? 2 : 1)));
@@ -56,11 +70,9 @@ HbmPlan hbm_plan(int64_t B, int n, int K, int mode) {
     if (sc > 4096) sc = 4096;
     if (sc > B) sc = B > 0 ? B : 1;
     pl.Sc = sc;
-    const int64_t T = (int64_t)1 << pl.tiles_log2;
-    pl.smem_fwd = (size_t)(8 << kTileBits);          // psi tile: 64 KB -> two forward CTAs per SM
-    pl.smem_rev = (size_t)(8 << kTileBits) * 2;      // psi + lam tiles
-    auto kf = hea_hbm_pass_kernel<false>;
-    auto kr = hea_hbm_pass_kernel<true>;
+    pl.smem_fwd = (size_t)8 << pl.tb_fwd;              // psi tile
+    pl.smem_rev = (size_t)16 << pl.tb_rev;             // psi + lam tiles
+    PassKern kf = pass_kernel(false, pl.tb_fwd), kr = pass_kernel(true, pl.tb_rev);
     if (cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_fwd) != cudaSuccess ||
         cudaFuncSetAttribute(kr, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_rev) != cudaSuccess) {
         cudaGetLastError();
@@ -69,20 +81,21 @@ HbmPlan hbm_plan(int64_t B, int n, int K, int mode) {
     int of = 0, orv = 0, sms = 0, dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&of, kf, kHbmThreads, pl.smem_fwd) != cudaSuccess || of < 1 ||
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&orv, kr, kHbmThreads, pl.smem_rev) != cudaSuccess || orv < 1) {
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&of, kf, 1 << (pl.tb_fwd - 5), pl.smem_fwd) != cudaSuccess || of < 1 ||
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&orv, kr, 1 << (pl.tb_rev - 5), pl.smem_rev) != cudaSuccess || orv < 1) {
         cudaGetLastError();
         return pl;
     }
     pl.grid_fwd = sms * of;
     pl.grid_rev = sms * orv;
-    pl.rows = pl.grid_rev * (kHbmThreads / 32);
+    pl.rows = pl.grid_rev * ((1 << (pl.tb_rev - 5)) / 32);
+    const int64_t Tm = (int64_t)1 << (n - kMeasureBits), Tr = (int64_t)1 << (n - pl.tb_rev);
     size_t off = 0;
     pl.off_psi = off; off = up256(off + (size_t)sc * state);
     pl.off_lam = off; if (grad) off = up256(off + (size_t)sc * state);
-    pl.off_epart = off; off = up256(off + (size_t)sc * T * sizeof(float));
+    pl.off_epart = off; off = up256(off + (size_t)sc * Tm * sizeof(float));
     pl.off_gval = off; off = up256(off + (size_t)sc * sizeof(float));
-    pl.off_mx = off; if (mode == 1) off = up256(off + (size_t)sc * T * 3 * n * K * sizeof(float));
+    pl.off_mx = off; if (mode == 1) off = up256(off + (size_t)sc * Tr * 3 * n * K * sizeof(float));
     pl.bytes = off;
     pl.ok = true;
     return pl;
@@ -97,26 +110,29 @@ cudaError_t hbm_run(const HeaParams<float>& p, const int* depth, int n, int K, i
     hb.epart = (float*)(ws + pl.off_epart);
     hb.gval = (float*)(ws + pl.off_gval);
     hb.mxpart = need_gx ? (float*)(ws + pl.off_mx) : nullptr;
-    const int64_t N = (int64_t)1 << n, T = (int64_t)1 << pl.tiles_log2;
-    auto kf = hea_hbm_pass_kernel<false>;
-    auto kr = hea_hbm_pass_kernel<true>;
+    const int64_t N = (int64_t)1 << n;
+    const int tbf = pl.tb_fwd, tbr = pl.tb_rev;
+    const int thr_f = 1 << (tbf - 5), thr_r = 1 << (tbr - 5);
+    PassKern kf = pass_kernel(false, tbf), kr = pass_kernel(true, tbr);
     cudaError_t e;
     if ((e = cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_fwd)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(kr, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_rev)) != cudaSuccess) return e;
 
     HbmPass A_f, B_f, A_r, B_r;
-    make_pass(A_f, n, false, false);
-    make_pass(B_f, n, true, false);
-    make_pass(A_r, n, false, true);
-    make_pass(B_r, n, true, true);
+    make_pass(A_f, n, tbf, false, false);
+    make_pass(B_f, n, tbf, true, false);
+    make_pass(A_r, n, tbr, false, true);
+    make_pass(B_r, n, tbr, true, true);
 
     for (int64_t b0 = 0; b0 < p.B; b0 += pl.Sc) {
         const int64_t nb = p.B - b0 < pl.Sc ? p.B - b0 : pl.Sc;
-        const int64_t tiles = nb * T;
-        auto grid_for = [&](int cap) { return (int)(tiles < cap ? tiles : cap); };
-        auto fill = [&](HbmPass hp, int s, int k, int j, bool reverse) {
-            hp.s = s; hp.kblk = k; hp.fold = j == 0; hp.reverse = reverse;
-            hp.ring_store = 0; hp.ring_load = 0; hp.scale_lam = 0; hp.tiles_log2 = pl.tiles_log2;
+        auto grid_for = [&](int tb, int cap) {
+            const int64_t tiles = nb << (n - tb);
+            return (int)(tiles < cap ? tiles : cap);
+        };
+        auto fill = [&](HbmPass hp, int tb, int s, int k, int j) {
+            hp.s = s; hp.kblk = k; hp.fold = j == 0;
+            hp.ring_store = 0; hp.ring_load = 0; hp.tiles_log2 = n - tb;
             hp.need_gx = need_gx; hp.b0 = b0; hp.nb = nb;
             return hp;
         };
@@ -128,35 +144,33 @@ cudaError_t hbm_run(const HeaParams<float>& p, const int* depth, int n, int K, i
         int s = 0;
         for (int k = 0; k < K; ++k)
             for (int j = 0; j < depth[k]; ++j, ++s) {
-                HbmPass a = fill(A_f, s, k, j, false);
-                kf<<<grid_for(pl.grid_fwd), kHbmThreads, pl.smem_fwd, st>>>(p, a, hb);
-                HbmPass b = fill(B_f, s, k, j, false);
+                HbmPass a = fill(A_f, tbf, s, k, j);
+                kf<<<grid_for(tbf, pl.grid_fwd), thr_f, pl.smem_fwd, st>>>(p, a, hb);
+                HbmPass b = fill(B_f, tbf, s, k, j);
                 b.ring_store = 1;
-                kf<<<grid_for(pl.grid_fwd), kHbmThreads, pl.smem_fwd, st>>>(p, b, hb);
+                kf<<<grid_for(tbf, pl.grid_fwd), thr_f, pl.smem_fwd, st>>>(p, b, hb);
             }
         {
-            const int g = (int)(tiles < 4 * 148 ? tiles : 4 * 148);
-            if (grad) hea_hbm_measure_kernel<true><<<g, 256, 0, st>>>(p, n, pl.tiles_log2, nb, hb);
-            else hea_hbm_measure_kernel<false><<<g, 256, 0, st>>>(p, n, pl.tiles_log2, nb, hb);
-            hea_hbm_seed_kernel<<<(int)((nb + 127) / 128), 128, 0, st>>>(p, pl.tiles_log2, b0, nb, hb, grad ? 1 : 0);
+            const int64_t mt = nb << (n - kMeasureBits);
+            const int g = (int)(mt < 4 * 148 ? mt : 4 * 148);
+            if (grad) hea_hbm_measure_kernel<true><<<g, 256, 0, st>>>(p, n, nb, hb);
+            else hea_hbm_measure_kernel<false><<<g, 256, 0, st>>>(p, n, nb, hb);
+            hea_hbm_seed_kernel<<<(int)((nb + 127) / 128), 128, 0, st>>>(p, n, b0, nb, hb, grad ? 1 : 0);
         }
         if (grad) {
-            bool first = true;
             for (int k = K - 1; k >= 0; --k)
                 for (int j = depth[k] - 1; j >= 0; --j) {
                     --s;
-                    HbmPass b = fill(B_r, s, k, j, true);
+                    HbmPass b = fill(B_r, tbr, s, k, j);
                     b.ring_load = 1;
-                    b.scale_lam = first ? 1 : 0;
-                    first = false;
-                    kr<<<grid_for(pl.grid_rev), kHbmThreads, pl.smem_rev, st>>>(p, b, hb);
-                    HbmPass a = fill(A_r, s, k, j, true);
-                    kr<<<grid_for(pl.grid_rev), kHbmThreads, pl.smem_rev, st>>>(p, a, hb);
+                    kr<<<grid_for(tbr, pl.grid_rev), thr_r, pl.smem_rev, st>>>(p, b, hb);
+                    HbmPass a = fill(A_r, tbr, s, k, j);
+                    kr<<<grid_for(tbr, pl.grid_rev), thr_r, pl.smem_rev, st>>>(p, a, hb);
                 }
             if (need_gx) {
                 int64_t blocks = (nb * n * K + 255) / 256;
                 if (blocks > 2048) blocks = 2048;
-                hea_hbm_gx_kernel<<<(int)blocks, 256, 0, st>>>(p, n, pl.tiles_log2, b0, nb, hb);
+                hea_hbm_gx_kernel<<<(int)blocks, 256, 0, st>>>(p, n, n - tbr, b0, nb, hb);
             }
         }
         if ((e = cudaGetLastError()) != cudaSuccess) return e;

@@ -1,52 +1,53 @@
 // HBM-streamed tier (fp32, n = 14 ... 22): the states of a chunk of samples live in the HBM workspace and
-// are streamed through shared memory in TILES of 2^13 amplitudes (64 KB of psi, + 64 KB of lam in the
-// reverse sweep).  One ansatz sublayer = TWO passes over HBM, each a kernel launch over all tiles of the chunk:
+// are streamed through shared memory in TILES of 2^TB amplitudes (TB = 12 or 13: 32 / 64 KB of psi, twice
+// that with lam in the reverse sweep).  One ansatz sublayer = TWO passes over HBM, each a kernel launch
+// over all tiles of the chunk:
 //
-//   pass A  tile = 2^13 contiguous amplitudes          -> gates on qubits 0..12   (windows [0,5) [5,10) [8,13))
-//   pass B  tile = 2^c-amplitude contiguous chunks x the n-13 high qubits (c = 26-n)
-//                                                      -> gates on qubits 13..n-1, then the CNOT ring as a
-//                                                         GF(2)-linear scatter on the way back to HBM
+//   pass A  tile = 2^TB contiguous amplitudes           -> gates on qubits 0..TB-1 (windows [0,5) [5,10) [TB-5,TB))
+//   pass B  tile = 2^c-amplitude contiguous chunks x the n-TB high qubits (c = 2 TB - n)
+//                                                       -> gates on qubits TB..n-1, then the CNOT ring as a
+//                                                          GF(2)-linear scatter on the way back to HBM
 //
 // Inside a tile the register-blocked FFMA2 window passes of the shared-memory tier (hea_smem.cuh) are reused
-// unchanged (same swizzle, same constant-memory offset tables, n = 13 geometry); windows always run five
-// gates and take identity coefficients for bits that carry no gate in this pass (pass B is HBM-bound, so
-// the padding is free; pass A wastes 2 of 15).  Algorithmic HBM traffic: 2 x (read + write) x 8 B x 2^n per
-// sublayer forward, 2 x that in the reverse sweep (psi and lam); the encoding layers cost none (RX folded).
+// (same swizzle, same constant-memory offset tables, n = TB geometry, 2^(TB-5) threads per tile); windows
+// always run five gates and take identity coefficients for bits that carry no gate in this pass (pass B is
+// HBM-bound, so the padding is free).  Tiles travel HBM -> shared memory with 8-byte cp.async straight into
+// the swizzled slots.  Smaller tiles (TB = 12) put 4 forward / 2 reverse CTAs on an SM, so one CTA's HBM
+// phase overlaps another's FP32 phase.  Algorithmic HBM traffic: 2 x (read + write) x 8 B x 2^n per sublayer
+// forward, 2 x that in the reverse sweep (psi and lam); the encoding layers cost none (RX folded).
 //
 // The reverse sweep runs the same two passes backwards on (psi, lam): pass B first (gathers through the
-// ring permutation), then pass A; shared-parameter moments go to the per-warp rows as in the other tiers,
-// per-sample dL/dx moments go to a per-(sample, tile) partial buffer summed in fixed order afterwards.
+// ring permutation), then pass A; lam stays unscaled (= H psi) and the per-sample upstream gradient g
+// multiplies the moments where they are consumed.  Shared-parameter moments go to the per-warp rows as in
+// the other tiers, per-sample dL/dx moments to a per-(sample, tile) partial buffer summed in fixed order.
 // Reference semantics: core/quantum_circuits_tq.py:65-127.
 #pragma once
 #include "hea_smem.cuh"
 
 namespace qon {
 
-constexpr int kTileBits = 13;
-constexpr int kTileAmps = 1 << kTileBits;
-constexpr int kHbmThreads = 256;
+constexpr int kMaxTileBits = 13;
+constexpr int kMeasureBits = 13;          // granularity of the expectation-value partials (independent of TB)
 
 struct HbmPass {
-    int n, c;                     // c = contiguous low bits of a tile chunk (13 for pass A, 26 - n for pass B)
+    int n, c;                     // c = contiguous low bits of a tile chunk (TB for pass A, 2 TB - n for pass B)
     int nwin;                     // windows to run, in execution order
-    int win[3], mask[3];          // window index into the n = 13 tables (lo = 0, 5, 8) and its gate mask
+    int win[3], mask[3];          // window index into the n = TB tables and its gate mask
     int qoff;                     // qubit of local bit l (for gated bits) = l + qoff
     int s, kblk, fold;            // sublayer, block (x columns kblk*n ..), RX folded into this sublayer
-    int reverse;                  // 0 forward (psi only), 1 reverse (psi and lam, moments)
     int ring_store, ring_load;    // scatter / gather through the CNOT-ring permutation
-    int scale_lam;                // multiply lam by g[sample] while loading (first reverse pass)
-    int tiles_log2;               // log2(tiles per sample) = n - 13
+    int tiles_log2;               // log2(tiles per sample) = n - TB
     int need_gx;
     int64_t b0, nb;               // first sample of the chunk, samples in the chunk
-    unsigned ringp[kTileBits];    // ring(gidx(e_l)) for the 13 local bits
+    unsigned ringp[kMaxTileBits]; // ring(gidx(e_l)) for the TB local bits
 };
 
 struct HbmBuffers {
     u64* psi;          // [Sc][2^n]
     u64* lam;          // [Sc][2^n]            (reverse only)
-    float* epart;      // [Sc][T]
+    float* epart;      // [Sc][2^(n-13)]
     float* gval;       // [Sc]                 upstream gradient per sample
-    float* mxpart;     // [Sc][T][3*n*K]       per-tile Pauli moments of the folded RX gates
+    float* mxpart;     // [Sc][T][3*n*K]       per-tile Pauli moments of the folded RX gates (T = reverse tiles)
 };
 
 __device__ __forceinline__ void cp_async8(unsigned smem_addr, const void* gptr) {
@@ -54,7 +55,7 @@ __device__ __forceinline__ void cp_async8(unsigned smem_addr, const void* gptr) 
 }
 
 // window group <-> shared-memory tile; the tile base is ADDED (not XORed as in hea_smem.cuh) so the tile
-// needs no size alignment and two forward CTAs fit in one SM's shared memory
+// needs no size alignment
 __device__ __forceinline__ void tile_load(SmemState& st, unsigned region, unsigned gb, const int* off) {
 #pragma unroll
     for (int i = 0; i < 32; ++i) st.a[i] = lds64(region + (gb ^ (unsigned)off[i]));
@@ -64,28 +65,29 @@ __device__ __forceinline__ void tile_store(const SmemState& st, unsigned region,
     for (int i = 0; i < 32; ++i) sts64(region + (gb ^ (unsigned)off[i]), st.a[i]);
 }
 
-__device__ __forceinline__ unsigned hbm_ring(unsigned k, int n) {
+__host__ __device__ __forceinline__ unsigned hbm_ring(unsigned k, int n) {
     for (int i = 0; i < n; ++i) k ^= ((k >> (i + 1 == n ? 0 : i + 1)) & 1u) << i;
     return k;
 }
-// global amplitude index of local index l in tile t
-__device__ __forceinline__ unsigned hbm_gidx(unsigned l, unsigned t, int c) {
-    return (l & ((1u << c) - 1u)) | (t << c) | ((l >> c) << kTileBits);
+// global amplitude index of local index l in tile t (TB-bit tiles)
+template <int TB>
+__host__ __device__ __forceinline__ unsigned hbm_gidx(unsigned l, unsigned t, int c) {
+    return (l & ((1u << c) - 1u)) | (t << c) | ((l >> c) << TB);
 }
 
-template <bool REVERSE>
-__global__ void __launch_bounds__(kHbmThreads, REVERSE ? 1 : 2) hea_hbm_pass_kernel(const HeaParams<float> p, const HbmPass hp,
-                                                                      const HbmBuffers hb) {
+template <bool REVERSE, int TB>
+__global__ void __launch_bounds__(1 << (TB - 5), REVERSE ? (TB == 13 ? 1 : 2) : (TB == 13 ? 2 : 4))
+hea_hbm_pass_kernel(const HeaParams<float> p, const HbmPass hp, const HbmBuffers hb) {
     using State = SmemState;
+    constexpr int THREADS = 1 << (TB - 5);
+    constexpr int WARPS = THREADS / 32;
+    constexpr int TIDB = TB - 5;                       // local bits that come from the thread index when streaming
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ float s_red[kHbmThreads / 32][16];
-    constexpr int WARPS = kHbmThreads / 32;
+    __shared__ float s_red[WARPS][16];
     const int n = hp.n, c = hp.c;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const unsigned raw = (unsigned)__cvta_generic_to_shared(smem_raw);
-    const unsigned rb = 8u << kTileBits;
-    const unsigned psi_base = raw;   // addresses are base + (group ^ offset): no alignment slack, 2 forward CTAs per SM
-    const unsigned lam_base = psi_base + rb;
+    const unsigned psi_base = (unsigned)__cvta_generic_to_shared(smem_raw);
+    const unsigned lam_base = psi_base + (8u << TB);
     const int VP = (3 * n + 3) / 4 * 4;
     const int64_t gwarp = (int64_t)blockIdx.x * WARPS + warp;
     float* mrow = REVERSE ? p.mpart + gwarp * p.rowlen : nullptr;
@@ -97,6 +99,14 @@ __global__ void __launch_bounds__(kHbmThreads, REVERSE ? 1 : 2) hea_hbm_pass_ker
         const int kb = ((tid >> lo) << (lo + kSmemW)) | (tid & ((1 << lo) - 1));
         return (unsigned)(8 * smem_swz(kb));
     };
+    // ring(gidx(l)) is GF(2)-linear in l = tid + THREADS * r: thread part once per tile, r part = constants
+    auto ring_base = [&](unsigned t) -> unsigned {
+        unsigned v = hbm_ring(hbm_gidx<TB>(0u, t, c), n);
+#pragma unroll
+        for (int bit = 0; bit < TIDB; ++bit)
+            if ((tid >> bit) & 1) v ^= hp.ringp[bit];
+        return v;
+    };
 
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int64_t sl = tile >> hp.tiles_log2;            // sample slot in the chunk
@@ -106,32 +116,22 @@ __global__ void __launch_bounds__(kHbmThreads, REVERSE ? 1 : 2) hea_hbm_pass_ker
         u64* gpsi_w = hb.psi + sl * N;
         const u64* glam = REVERSE ? hb.lam + sl * N : nullptr;
         u64* glam_w = REVERSE ? hb.lam + sl * N : nullptr;
-        // lam is carried UNSCALED (= H psi) through the reverse sweep; the upstream gradient g of this tile's
-        // sample multiplies the moments where they are consumed (they are linear in lam)
         const float gsample = REVERSE ? hb.gval[sl] : 1.f;
 
-        // ---------------- HBM -> shared memory: cp.async straight into the swizzled slots (no register
-        // staging, all 32 (64) copies of a thread in flight at once); gather through the ring when asked ------
+        // ---------------- HBM -> shared memory ----------------
         {
-            // ring(gidx(l)) is GF(2)-linear in l = tid + 256 r: thread part once per tile, r part = constants
-            unsigned tbase_ring = 0u;
-            if (hp.ring_load) {
-                tbase_ring = hbm_ring(hbm_gidx(0u, t, c), n);
-#pragma unroll
-                for (int bit = 0; bit < 8; ++bit)
-                    if ((tid >> bit) & 1) tbase_ring ^= hp.ringp[bit];
-            }
+            const unsigned rbase = hp.ring_load ? ring_base(t) : 0u;
 #pragma unroll
             for (int r = 0; r < 32; ++r) {
-                const unsigned l = (unsigned)(tid + 256 * r);      // consecutive lanes -> consecutive amplitudes
+                const unsigned l = (unsigned)(tid + THREADS * r);      // consecutive lanes -> consecutive amplitudes
                 unsigned src;
                 if (hp.ring_load) {
-                    src = tbase_ring;
+                    src = rbase;
 #pragma unroll
-                    for (int bit = 8; bit < kTileBits; ++bit)
-                        if ((r >> (bit - 8)) & 1) src ^= hp.ringp[bit];
+                    for (int bit = 0; bit < 5; ++bit)
+                        if ((r >> bit) & 1) src ^= hp.ringp[TIDB + bit];
                 } else {
-                    src = hbm_gidx(l, t, c);
+                    src = hbm_gidx<TB>(l, t, c);
                 }
                 const unsigned slot = (unsigned)(8 * smem_swz((int)l));
                 cp_async8(psi_base + slot, gpsi + src);
@@ -147,9 +147,9 @@ __global__ void __launch_bounds__(kHbmThreads, REVERSE ? 1 : 2) hea_hbm_pass_ker
 #pragma unroll 1
         for (int wdx = 0; wdx < hp.nwin; ++wdx) {
             const int pw = hp.win[wdx], mask = hp.mask[wdx];
-            const int lo = pw == 0 ? 0 : (pw == 1 ? 5 : 8);
+            const int lo = smem_lo(TB, pw);
             const unsigned gb = group_base(lo);
-            const int* off = c_smem_tbl.off[kTileBits][pw];
+            const int* off = c_smem_tbl.off[TB][pw];
             State st;
             tile_load(st, psi_base, gb, off);
             if constexpr (!REVERSE) {
@@ -205,30 +205,22 @@ __global__ void __launch_bounds__(kHbmThreads, REVERSE ? 1 : 2) hea_hbm_pass_ker
 
         // ---------------- shared memory -> HBM (scatter through the ring when asked) ----------------
         {
-            unsigned tbase_ring = 0u;
-            if (hp.ring_store) {
-                tbase_ring = hbm_ring(hbm_gidx(0u, t, c), n);
-#pragma unroll
-                for (int bit = 0; bit < 8; ++bit)
-                    if ((tid >> bit) & 1) tbase_ring ^= hp.ringp[bit];
-            }
+            const unsigned rbase = hp.ring_store ? ring_base(t) : 0u;
 #pragma unroll 8
             for (int r = 0; r < 32; ++r) {
-                {
-                    const unsigned l = (unsigned)(tid + 256 * r);
-                    unsigned dst;
-                    if (hp.ring_store) {
-                        dst = tbase_ring;
+                const unsigned l = (unsigned)(tid + THREADS * r);
+                unsigned dst;
+                if (hp.ring_store) {
+                    dst = rbase;
 #pragma unroll
-                        for (int bit = 8; bit < kTileBits; ++bit)
-                            if ((r >> (bit - 8)) & 1) dst ^= hp.ringp[bit];
-                    } else {
-                        dst = hbm_gidx(l, t, c);
-                    }
-                    const unsigned slot = (unsigned)(8 * smem_swz((int)l));
-                    gpsi_w[dst] = lds64(psi_base + slot);
-                    if constexpr (REVERSE) glam_w[dst] = lds64(lam_base + slot);
+                    for (int bit = 0; bit < 5; ++bit)
+                        if ((r >> bit) & 1) dst ^= hp.ringp[TIDB + bit];
+                } else {
+                    dst = hbm_gidx<TB>(l, t, c);
                 }
+                const unsigned slot = (unsigned)(8 * smem_swz((int)l));
+                gpsi_w[dst] = lds64(psi_base + slot);
+                if constexpr (REVERSE) glam_w[dst] = lds64(lam_base + slot);
             }
         }
         __syncthreads();
@@ -242,18 +234,18 @@ __global__ void hea_hbm_init_kernel(u64* psi, int64_t N, int64_t nb) {
         psi[i] = (i % N) == 0 ? pack2(1.f, 0.f) : 0ull;
 }
 
-// E partials per (sample, tile of 8192 contiguous amplitudes); lam = H psi for the reverse sweep
+// E partials per (sample, chunk of 2^13 contiguous amplitudes); lam = H psi for the reverse sweep
 template <bool GRAD>
-__global__ void __launch_bounds__(256) hea_hbm_measure_kernel(const HeaParams<float> p, int n, int tiles_log2, int64_t nb,
+__global__ void __launch_bounds__(256) hea_hbm_measure_kernel(const HeaParams<float> p, int n, int64_t nb,
                                                               const HbmBuffers hb) {
     __shared__ float red[8];
-    const int64_t T = (int64_t)1 << tiles_log2, N = (int64_t)1 << n;
+    const int64_t T = (int64_t)1 << (n - kMeasureBits), N = (int64_t)1 << n;
     for (int64_t tile = blockIdx.x; tile < nb * T; tile += gridDim.x) {
-        const int64_t sl = tile >> tiles_log2, t = tile & (T - 1);
+        const int64_t sl = tile / T, t = tile % T;
         const u64* ps = hb.psi + sl * N;
         float e = 0.f;
-        for (int i = threadIdx.x; i < kTileAmps; i += blockDim.x) {
-            const int64_t k = t * kTileAmps + i;
+        for (int i = threadIdx.x; i < (1 << kMeasureBits); i += blockDim.x) {
+            const int64_t k = t * (1 << kMeasureBits) + i;
             const u64 v = ps[k];
             u64 h;
             if (p.pauli == 0) {
@@ -286,10 +278,10 @@ __global__ void __launch_bounds__(256) hea_hbm_measure_kernel(const HeaParams<fl
     }
 }
 
-// per sample: E = sum of tile partials (fixed order), out, upstream gradient g
-__global__ void hea_hbm_seed_kernel(const HeaParams<float> p, int tiles_log2, int64_t b0, int64_t nb, const HbmBuffers hb,
+// per sample: E = sum of the partials (fixed order), out, upstream gradient g
+__global__ void hea_hbm_seed_kernel(const HeaParams<float> p, int n, int64_t b0, int64_t nb, const HbmBuffers hb,
                                     int grad) {
-    const int64_t T = (int64_t)1 << tiles_log2;
+    const int64_t T = (int64_t)1 << (n - kMeasureBits);
     for (int64_t sl = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; sl < nb; sl += (int64_t)gridDim.x * blockDim.x) {
         float e = 0.f;
         for (int64_t t = 0; t < T; ++t) e += hb.epart[sl * T + t];
