@@ -26,7 +26,10 @@ struct RegK {
     static constexpr bool GX = MODE == 1;
     static constexpr int ENC = MODE < 3 ? 0 : (MODE == 5 ? 2 : 1);
     static constexpr int THREADS = GRAD ? QON_GRAD_THREADS : QON_FWD_THREADS;
-    static constexpr int MINB = GRAD ? 256 / QON_GRAD_THREADS : QON_FWD_MINB;
+#ifndef QON_GRAD_MINB
+#define QON_GRAD_MINB (256 / QON_GRAD_THREADS)
+#endif
+    static constexpr int MINB = GRAD ? QON_GRAD_MINB : QON_FWD_MINB;
     static void (*kernel())(const HeaParams<T>) { return hea_reg_kernel<T, NL, LQ, GRAD, GX, ENC, THREADS, MINB>; }
     static RegLaunchInfo info() {
         RegLaunchInfo r{THREADS, 0, 0, true};

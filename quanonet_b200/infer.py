@@ -110,3 +110,35 @@ def evaluate(y_pred: np.ndarray, y_true: np.ndarray) -> dict:
     diff = y_pred - y_true
     return {"rel_l2": float(np.linalg.norm(diff) / (np.linalg.norm(y_true) + 1e-8)),
             "mse": float(np.mean(diff ** 2)), "mae": float(np.mean(np.abs(diff)))}
+
+
+def main(argv=None):
+    """CLI in the shape of the reference's (``infer.py:333-427``): checkpoint + test data in, metrics out.
+    ``--data`` is an ``.npz`` with ``test_branch_input`` / ``test_trunk_input`` (or ``test_input``) and optionally
+    ``test_output``; auto-generating data is outside this package."""
+    import argparse
+    import json
+
+    ap = argparse.ArgumentParser(description="QuanONet / HEAQNN inference on the B200 kernels")
+    ap.add_argument("--ckpt", required=True)
+    ap.add_argument("--data", required=True)
+    ap.add_argument("--output", default=None, help="save predictions to this .npy")
+    ap.add_argument("--batch_size", type=int, default=262_144)
+    args = ap.parse_args(argv)
+    with np.load(args.data) as z:
+        branch = z["test_branch_input"] if "test_branch_input" in z.files else z["test_input"]
+        trunk = z["test_trunk_input"] if "test_trunk_input" in z.files else None
+        truth = z["test_output"] if "test_output" in z.files else None
+    model, cfg = load_model(args.ckpt, branch_in=branch.shape[1], trunk_in=None if trunk is None else trunk.shape[1])
+    pred = predict(model, branch, trunk, cfg, batch_size=args.batch_size)
+    print(f"Output: {pred.shape}")
+    if truth is not None:
+        print(json.dumps(evaluate(pred, np.asarray(truth).reshape(len(truth), -1)[:, :1])))
+    if args.output:
+        np.save(args.output, pred)
+    return 0
+
+
+if __name__ == "__main__":
+    import sys
+    sys.exit(main())

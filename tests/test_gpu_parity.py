@@ -517,3 +517,32 @@ def test_compare_backends_harness(cuda_device):
     r = subprocess.run([sys.executable, os.path.join(root, "tests", "harness", "compare_backends_b200.py")],
                        capture_output=True, text=True, timeout=900)
     assert r.returncode == 0 and "0 FAIL" in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
+
+
+def test_cli_entry_points(cuda_device, tmp_path):
+    """python -m quanonet_b200.train_cli / quanonet_b200.infer round trip on a tiny operator-learning task."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    rng = np.random.default_rng(4)
+    branch = rng.standard_normal((160, 5)); t = rng.random((160, 1)); y = np.cos(branch[:, :1]) * t
+    data = {"train_branch_input": branch, "train_trunk_input": t, "train_output": y,
+            "test_branch_input": branch[:40], "test_trunk_input": t[:40], "test_output": y[:40]}
+    np.savez(tmp_path / "data.npz", **data)
+    run_dir = tmp_path / "Demo_QuanONet_Net2-1-2-1_Q3_TF_S0.3_160x1_Seed0"
+    cfg = {"model_type": "QuanONet", "num_qubits": 3, "net_size": [2, 1, 2, 1], "scale_coeff": 0.3,
+           "if_trainable_freq": "true", "learning_rate": 0.02, "num_epochs": 5, "batch_size": 40,
+           "output_dir": str(run_dir), "quantum_backend": "torchquantum"}
+    json.dump(cfg, open(tmp_path / "cfg.json", "w"))
+    env = dict(os.environ, PYTHONPATH=root)
+    r = subprocess.run([sys.executable, "-m", "quanonet_b200.train_cli", "--config", str(tmp_path / "cfg.json"),
+                        "--data", str(tmp_path / "data.npz")], capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    out = json.loads(r.stdout.strip().splitlines()[-1])
+    assert out["epochs"] == 5 and np.isfinite(out["metrics"]["rel_l2"])
+    r = subprocess.run([sys.executable, "-m", "quanonet_b200.infer", "--ckpt", str(run_dir / "best_model.npz"),
+                        "--data", str(tmp_path / "data.npz"), "--output", str(tmp_path / "pred.npy")],
+                       capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0 and "Output: (40, 1)" in r.stdout, r.stdout + r.stderr
+    assert np.load(tmp_path / "pred.npy").shape == (40, 1)
