@@ -142,6 +142,11 @@ int qon_encoded_mse_step(const void* u0, int64_t ldu0, int in0, int K0, const vo
  * 2^lanes_log2 lanes per sample), 1 = shared-memory tier, 2 = HBM-streamed tier; -1 = unsupported. */
 int qon_plan_tier(int64_t B, int n, int dtype, int need_grad, int* lanes_log2);
 
+/* Largest batch (per call) that the small-batch latency tier serves (n <= 5, angles given: one amplitude per
+ * lane, see csrc/hea_warp.cuh); larger batches use the one-thread-per-sample throughput layout.  Callers that
+ * can choose between the x-given and the fused-encoding entry points use it to pick the faster one. */
+int64_t qon_latency_tier_max_batch(void);
+
 /* FP32 FFMA-saturating micro-benchmark (the metric is "% of FP32 peak" and MEASURED_PEAKS.json has
  * no FP32 entry): runs `iters` dependent-chain FFMA rounds on every SM and returns achieved
  * TFLOP/s measured with CUDA events on `stream`; negative on error.  Synchronises the stream. */

@@ -29,6 +29,7 @@ EXPORTED_SYMBOLS = (
     "qon_encoded_forward",
     "qon_encoded_mse_step",
     "qon_plan_tier",
+    "qon_latency_tier_max_batch",
     "qon_measure_fp32_peak_tflops",
 )
 
@@ -64,6 +65,8 @@ def _declare(lib):
     lib.qon_encoded_forward.argtypes = enc_head + [vp, vp, i64, i32, i32, ip] + ham_tail
     lib.qon_encoded_mse_step.restype = i32
     lib.qon_encoded_mse_step.argtypes = enc_head + [vp, vp, vp, dbl, vp, vp, vp, vp, vp, i64, i32, i32, ip] + ham_tail
+    lib.qon_latency_tier_max_batch.restype = i64
+    lib.qon_latency_tier_max_batch.argtypes = []
     lib.qon_plan_tier.restype = i32
     lib.qon_plan_tier.argtypes = [i64, i32, i32, i32, ip]
     lib.qon_measure_fp32_peak_tflops.restype = dbl

@@ -96,6 +96,10 @@ __device__ __forceinline__ void sincos_half(float t, float& s, float& c) {
 }
 __device__ __forceinline__ void sincos_half(double t, double& s, double& c) { sincos(0.5 * t, &s, &c); }
 
+// depth_per_block as a kernel parameter (constant bank: loop bounds read from it are provably warp-uniform)
+constexpr int kMaxBlocks = 1024;
+struct DepthPack { unsigned char d[kMaxBlocks]; };
+
 // geometry of the fp32 shared-memory tier (hea_smem.cuh)
 constexpr int kSmemMinN = 6, kSmemMaxN = 13, kSmemW = 5, kSmemMaxP = 3;
 struct SmemGeom {

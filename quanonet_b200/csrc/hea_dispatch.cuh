@@ -41,6 +41,18 @@ struct SmemPlan {
 SmemPlan smem_plan(int n, int mode);
 cudaError_t smem_launch(int mode, int grid, const SmemPlan& sp, const HeaParams<float>& p, cudaStream_t st);
 
+// small-batch latency tier (hea_warp.cu): one amplitude per lane, n in [1, 5], fp32 and fp64, modes 0 / 1 / 2
+struct WarpPlan {
+    bool ok;
+    int threads, blocks_per_sm;
+    size_t smem_bytes;
+};
+WarpPlan warp_plan(int n, int K, int S, int dtype_bytes, int mode);
+cudaError_t warp_launch_f32(int n, int mode, int grid, const WarpPlan& wp, const HeaParams<float>& p,
+                            const DepthPack& dp, cudaStream_t st);
+cudaError_t warp_launch_f64(int n, int mode, int grid, const WarpPlan& wp, const HeaParams<double>& p,
+                            const DepthPack& dp, cudaStream_t st);
+
 // fp32 HBM-streamed tier (hea_hbm.cu): n in [kHbmMinN, kHbmMaxN], modes 0 / 1 / 2
 constexpr int kHbmMinN = 14, kHbmMaxN = 22;
 struct HbmPlan {

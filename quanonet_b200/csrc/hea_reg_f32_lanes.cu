@@ -1,14 +1,12 @@
 // Register-tier kernel instantiations, fp32 / complex64, 2^LQ lanes per sample:
 //   (5, LQ)  n = 6..10 — the lane-distributed layout for mid-size circuits (the shared-memory tier is the
-//            default there; kept for A/B runs, QON_SMEM_FIRST_N);
-//   (0, n)   n = 1..5, one AMPLITUDE per lane — the small-batch latency layout: a batch of 100 samples
-//            (the reference's default, utils/common.py:128) fills 100 warps instead of 4, and the
-//            per-sample critical path drops from ~340k instructions to ~600 gate latencies.
+//            default there; kept for A/B runs, QON_SMEM_FIRST_N).
+// The one-amplitude-per-lane small-batch layout lives in hea_warp.cuh.
 #include "hea_reg_inst.cuh"
 
 namespace qon {
 
-#define QON_F32_LANE_COMBOS(X) X(5, 1) X(5, 2) X(5, 3) X(5, 4) X(5, 5) X(0, 1) X(0, 2) X(0, 3) X(0, 4) X(0, 5)
+#define QON_F32_LANE_COMBOS(X) X(5, 1) X(5, 2) X(5, 3) X(5, 4) X(5, 5)
 
 RegLaunchInfo reg_info_f32_lanes(int nl, int lq, int mode) {
 #define X(NL, LQ) if (nl == NL && lq == LQ) return reg_info_t<float, NL, LQ>(mode);

@@ -27,10 +27,7 @@ int fail(int code, const char* fmt, ...) {
     return code;
 }
 
-constexpr int kMaxBlocks = 1024;   // K limit: depth_per_block travels in kernel parameters
 constexpr int kMaxQubits = 24;
-
-struct DepthPack { unsigned char d[kMaxBlocks]; };
 
 // ---------------------------------------------------------------------------------------------
 // prep: per-(sublayer, qubit) gate tables, Hamiltonian diagonal, depth array, column -> source-row
@@ -233,7 +230,9 @@ inline size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
 int64_t lanes_max_batch() {
     static const int64_t v = [] {
         const char* e = getenv("QON_LANES_MAX_B");
-        return e ? (int64_t)atoll(e) : (int64_t)2048;   // measured: 280 us vs 900 us at B <= 1000, break-even ~4096
+        // measured (Q5, 120 sublayers, fwd+grad): 69 us at B = 100, 229 us at 4096, 449 us at 8192, 890 us at
+        // 16384 — where the one-thread-per-sample kernel (one ~900 us wave) draws level
+        return e ? (int64_t)atoll(e) : (int64_t)12288;
     }();
     return v;
 }
@@ -269,6 +268,8 @@ struct Plan {
     bool fast_smem = false;   // tier 1 served by hea_smem.cuh (fp32) instead of the generic kernel
     HbmPlan hp{};
     bool fast_hbm = false;    // tier 2 served by hea_hbm.cuh (fp32) instead of the generic kernel
+    WarpPlan wp{};
+    bool fast_warp = false;   // tier 0 served by hea_warp.cuh (one amplitude per lane, small batches)
     size_t off_u = 0, off_r = 0, off_h = 0, off_d = 0, off_i = 0, off_m = 0, off_state = 0, total = 0;
     int64_t rowlen = 0, mpart_len = 0;
 };
@@ -294,6 +295,7 @@ int make_plan(int64_t B, int n, int K, const int* depth, int dtype, int mode, Pl
     const int max_local = dtype == QON_F32 ? 5 : 4;
     pl->fast_smem = false;
     pl->fast_hbm = false;
+    pl->fast_warp = false;
     if (dtype == QON_F32 && !mode_is_enc(mode) && n >= smem_first_n(grad) && n <= kSmemMaxN) {
         // fp32 shared-memory tier: register-blocked FFMA2 passes over a state held in shared memory
         pl->sp = smem_plan(n, mode);
@@ -323,20 +325,29 @@ int make_plan(int64_t B, int n, int K, const int* depth, int dtype, int mode, Pl
         pl->tier = 0;
         pl->nl = n <= max_local ? n : max_local;
         pl->lq = n - pl->nl;
-        // small batches (fp32, n <= 5, x given): one amplitude per lane, 2^n lanes per sample — latency layout
-        if (dtype == QON_F32 && n <= max_local && !mode_is_enc(mode) && B <= lanes_max_batch()) {
+        // small batches (n <= 5, x given): one amplitude per lane, 2^n lanes per sample — the latency tier
+        if (n <= 5 && !mode_is_enc(mode) && B <= lanes_max_batch()) {
+            pl->wp = warp_plan(n, K, (int)S, (int)es, mode);
+            pl->fast_warp = pl->wp.ok;
+        }
+        int warps, blocks_per_sm;
+        if (pl->fast_warp) {
             pl->nl = 0;
             pl->lq = n;
+            warps = pl->wp.threads / 32;
+            blocks_per_sm = pl->wp.blocks_per_sm;
+        } else {
+            RegLaunchInfo ri = reg_info_cached(dev, dtype, pl->nl, pl->lq, mode);
+            if (!ri.ok)
+                return fail(QON_ERR_UNSUPPORTED, "register-tier kernel (n=%d, lanes 2^%d, mode %d) is not built%s", n,
+                            pl->lq, mode, mode_is_enc(mode) ? " (fused encoding needs n <= 5 in fp32, n <= 4 in fp64)" : "");
+            warps = ri.threads / 32;
+            blocks_per_sm = ri.blocks_per_sm;
         }
-        RegLaunchInfo ri = reg_info_cached(dev, dtype, pl->nl, pl->lq, mode);
-        if (!ri.ok)
-            return fail(QON_ERR_UNSUPPORTED, "register-tier kernel (n=%d, lanes 2^%d, mode %d) is not built%s", n,
-                        pl->lq, mode, mode_is_enc(mode) ? " (fused encoding needs n <= 5 in fp32, n <= 4 in fp64)" : "");
-        const int warps = ri.threads / 32;
         const int64_t spw = 32 >> pl->lq;
         const int64_t tiles = (B + spw - 1) / spw;
         int64_t grid = (tiles + warps - 1) / warps;
-        const int64_t cap = (int64_t)di.sms * ri.blocks_per_sm;
+        const int64_t cap = (int64_t)di.sms * blocks_per_sm;
         if (grid > cap) grid = cap;
         if (grid < 1) grid = 1;
         pl->grid = (int)grid;
@@ -465,7 +476,10 @@ int run(const Job& j) {
     }
     if (j.B > 0) {
         cudaError_t e;
-        if (pl.tier == 0) {
+        if (pl.fast_warp) {
+            if constexpr (sizeof(T) == 4) e = warp_launch_f32(n, mode, pl.grid, pl.wp, (const HeaParams<float>&)p, dp, st);
+            else e = warp_launch_f64(n, mode, pl.grid, pl.wp, (const HeaParams<double>&)p, dp, st);
+        } else if (pl.tier == 0) {
             if constexpr (sizeof(T) == 4) e = reg_launch_f32(pl.nl, pl.lq, mode, pl.grid, (const HeaParams<float>&)p, st);
             else e = reg_launch_f64(pl.nl, pl.lq, mode, pl.grid, (const HeaParams<double>&)p, st);
         } else if (pl.fast_smem) {
@@ -543,6 +557,8 @@ size_t qon_workspace_bytes(int64_t B, int n, int K, const int* depth_per_block, 
     }
     return total;
 }
+
+int64_t qon_latency_tier_max_batch(void) { return lanes_max_batch(); }
 
 int qon_plan_tier(int64_t B, int n, int dtype, int need_grad, int* lanes_log2) {
     int one = 1;

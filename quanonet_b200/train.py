@@ -88,7 +88,6 @@ class DataParallelTrainer:
         # whole-model fused kernel (frequency layers evaluated in-kernel, x / grad_x never materialised):
         # needs the register tier with one thread per sample and the standard n-angles-per-block layout
         self.kernel_events = None      # set to a list to collect (start, end) CUDA events around the kernel call
-        self.small_batch = 2048        # <= this many samples per rank: latency layout (keep equal to QON_LANES_MAX_B)
         self.fused_encoding = False
         if kernel_fn is None and use_fused_encoding and p0.is_cuda:
             from .ops import encoded_supported
@@ -106,9 +105,10 @@ class DataParallelTrainer:
         B = y.shape[0]
         gB = global_batch if global_batch is not None else B * self.world_size
         scale = 2.0 / gB
-        # Small fp32 batches take the x-given path: the library then spreads every sample over 2^n lanes
-        # (latency layout, csrc/hea_reg_f32_lanes.cu) — the fused-encoding kernels are one-thread-per-sample.
-        small = B <= self.small_batch and q.ansatz_weights.dtype == torch.float32
+        # Small batches take the x-given path: the library then spreads every sample over 2^n lanes (latency
+        # tier, csrc/hea_warp.cuh) — the fused-encoding kernels are one-thread-per-sample.
+        from .ops import use_latency_tier
+        small = use_latency_tier(B, q.n_wires)
         if self.fused_encoding and not small:
             return self._compute_grads_fused(inputs, y, scale, gB)
         if self.is_onet:

@@ -49,10 +49,11 @@ def test_circuit_cases_match_golden(cuda_device, dtype, tol):
         e, gx, gw = _run_case(tag, m, z, dtype, cuda_device)
         errs = (rel_l2(e, z[f"{tag}/e"]), rel_l2(gx, z[f"{tag}/gx"]), rel_l2(gw, z[f"{tag}/gw"]))
         worst[tag] = errs
-        if dtype == torch.float32 and m["n"] <= 5:
-            # small batches use the 2^n-lanes-per-sample latency layout; tile the batch above its threshold to
-            # run the same case through the one-thread-per-sample FFMA2 kernel as well
-            reps = 4096 // z[f"{tag}/x"].shape[0] + 1
+        if m["n"] <= 5:
+            # small batches run on the 2^n-lanes-per-sample latency tier; tile the batch above its threshold to
+            # run the same case through the one-thread-per-sample throughput kernels as well
+            from quanonet_b200.ops import latency_tier_max_batch
+            reps = latency_tier_max_batch() // z[f"{tag}/x"].shape[0] + 1
             zt = {f"{tag}/x": np.tile(z[f"{tag}/x"], (reps, 1)), f"{tag}/w": z[f"{tag}/w"],
                   f"{tag}/g": np.tile(z[f"{tag}/g"], reps), f"{tag}/gx": np.tile(z[f"{tag}/gx"], (reps, 1))}
             e2, gx2, gw2 = _run_case(tag, m, zt, dtype, cuda_device)
@@ -546,3 +547,52 @@ def test_cli_entry_points(cuda_device, tmp_path):
                        capture_output=True, text=True, env=env, timeout=600)
     assert r.returncode == 0 and "Output: (40, 1)" in r.stdout, r.stdout + r.stderr
     assert np.load(tmp_path / "pred.npy").shape == (40, 1)
+
+
+def test_throughput_tier_on_small_batches(cuda_device):
+    """Small batches default to the latency tier (csrc/hea_warp.cuh).  Re-run the small-batch parity tests in a
+    subprocess with the latency tier disabled, so the one-thread-per-sample kernels (ragged tails, edge cases,
+    wrapper cases) stay covered at those sizes too."""
+    import subprocess, sys
+    env = dict(os.environ, QON_LANES_MAX_B="0")
+    here = os.path.abspath(__file__)
+    r = subprocess.run([sys.executable, "-m", "pytest", here, "-q", "-x", "-m", "gpu", "-k",
+                        "golden or edge or wrapper or published or closed_form or encoding"],
+                       env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+
+
+def test_latency_tier_all_widths(cuda_device):
+    """Latency tier, n = 1..5, fp32 and fp64, every observable kind, ragged batch (B not a multiple of the
+    samples-per-warp), mixed block depths (1, 2, 3) — against the fp64 oracle."""
+    from oracle import hea_oracle as O
+    from quanonet_b200.ops import hea_expval_backward, plan_tier, latency_tier_max_batch
+    rng = np.random.default_rng(11)
+    assert latency_tier_max_batch() >= 64
+    for n in (1, 2, 3, 4, 5):
+        depths = [1, 2, 3, 1, 2]
+        K, S = len(depths), sum(depths)
+        B = 37
+        x = rng.uniform(-np.pi, np.pi, (B, n * K)).astype(np.float32)
+        w = rng.uniform(-np.pi, np.pi, (S, 3, n)).astype(np.float32)
+        g = rng.standard_normal(B).astype(np.float32)
+        for kind in (0, 1, 2):
+            if kind == 0:
+                diag = rng.uniform(-2, 2, 1 << n)
+                ham = O.ham_from_diag(diag, n)
+                hd, off, co = diag, 0.0, 1.0
+            else:
+                off, co = 0.3, 0.7
+                ham = O.Ham("pauli", "X" if kind == 1 else "Y", off, co)
+                hd = None
+            e_ref, gx_ref, gw_ref = O.hea_forward_backward(x.astype(np.float64), w.astype(np.float64), n,
+                                                           [(n, d) for d in depths], ham, g.astype(np.float64))
+            for dtype, tol in ((torch.float32, TOL_F32), (torch.float64, TOL_F64)):
+                assert plan_tier(B, n, dtype) == (0, n)
+                xt = torch.tensor(x, dtype=dtype, device=cuda_device)
+                wt = torch.tensor(w, dtype=dtype, device=cuda_device)
+                gt = torch.tensor(g, dtype=dtype, device=cuda_device)
+                hdt = None if hd is None else torch.tensor(hd, dtype=dtype, device=cuda_device)
+                e, gx, gw = hea_expval_backward(gt, xt, wt, n, depths, hdt, 0, off, co, kind, True)
+                errs = (rel_l2(e.cpu().numpy()[:, 0], e_ref), rel_l2(gx.cpu().numpy(), gx_ref), rel_l2(gw.cpu().numpy(), gw_ref))
+                assert max(errs) < tol, (n, kind, dtype, errs)
