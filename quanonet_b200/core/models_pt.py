@@ -71,10 +71,8 @@ def _can_fuse_inference(qlayer, u):
     kernel (``quanonet::encoded_expval``) instead of materialising the encoding matrix."""
     if torch.is_grad_enabled() or not u.is_cuda:
         return False
-    from ..ops import encoded_supported, use_latency_tier
+    from ..ops import encoded_supported
     w = qlayer.ansatz_weights
-    if use_latency_tier(u.shape[0], qlayer.n_wires):
-        return False     # small batches: the x-given path runs on the 2^n-lanes-per-sample latency tier
     return (encoded_supported(qlayer.n_wires, w.dtype)
             and all(e == qlayer.n_wires and d >= 1 for e, d in qlayer.block_configs))
 

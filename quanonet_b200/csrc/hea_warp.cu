@@ -1,4 +1,5 @@
-// Small-batch latency tier: instantiations, planning and launch (fp32 and fp64, n = 1..5).
+// Small-batch latency tier: instantiations, planning and launch (fp32 and fp64, n = 1..5, modes 0..5 as in
+// hea_reg_inst.cuh).
 #include "hea_dispatch.cuh"
 #include "hea_warp.cuh"
 
@@ -11,9 +12,12 @@ using WarpKern = void (*)(const HeaParams<T>, const DepthPack);
 template <typename T, int N>
 WarpKern<T> warp_kernel_n(int mode) {
     switch (mode) {
-        case 0: return hea_warp_kernel<T, N, false, false, kWarpThreads>;
-        case 1: return hea_warp_kernel<T, N, true, true, kWarpThreads>;
-        case 2: return hea_warp_kernel<T, N, true, false, kWarpThreads>;
+        case 0: return hea_warp_kernel<T, N, false, false, 0, kWarpThreads>;
+        case 1: return hea_warp_kernel<T, N, true, true, 0, kWarpThreads>;
+        case 2: return hea_warp_kernel<T, N, true, false, 0, kWarpThreads>;
+        case 3: return hea_warp_kernel<T, N, false, false, 1, kWarpThreads>;
+        case 4: return hea_warp_kernel<T, N, true, false, 1, kWarpThreads>;
+        case 5: return hea_warp_kernel<T, N, true, false, 2, kWarpThreads>;
         default: return nullptr;
     }
 }
@@ -36,7 +40,7 @@ WarpPlan plan_t(int n, int K, int S, int mode) {
     WarpKern<T> k = warp_kernel<T>(n, mode);
     if (!k) return wp;
     wp.threads = kWarpThreads;
-    wp.smem_bytes = warp_smem_bytes<T>(n, K, S, mode == 1, kWarpThreads);
+    wp.smem_bytes = warp_smem_bytes<T>(n, K, S, mode == 1 || mode == 5, mode == 5, kWarpThreads);
     if (wp.smem_bytes > 200 * 1024) return wp;             // very long circuits: the throughput layout serves them
     if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wp.smem_bytes) != cudaSuccess ||
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&wp.blocks_per_sm, k, kWarpThreads, wp.smem_bytes) != cudaSuccess ||

@@ -27,14 +27,19 @@ constexpr int kWarpThreads = 128;
 template <typename T> struct alignas(2 * sizeof(T)) Vec2 { T x, y; };
 
 template <typename T>
-__host__ __device__ inline size_t warp_smem_bytes(int n, int K, int S, bool need_gx, int threads) {
-    const size_t tbl = (size_t)S * n * sizeof(Vec4<T>) * (need_gx ? 2 : 1);
-    const size_t sc = (size_t)(threads / 32) * (32 >> n) * (size_t)K * n * 2 * sizeof(T);
-    return tbl + sc;
+__host__ __device__ inline size_t warp_smem_bytes(int n, int K, int S, bool want_gx, bool freq_grad, int threads) {
+    const size_t tbl = (size_t)S * n * sizeof(Vec4<T>) * (want_gx ? 2 : 1);
+    const size_t per_sample = (size_t)K * n * (freq_grad ? 3 : 2) * sizeof(T);   // (sin, cos) [+ source value u]
+    return tbl + (size_t)(threads / 32) * (32 >> n) * per_sample;
 }
 
-template <typename T, int N, bool GRAD, bool NEED_GX, int THREADS>
+//   ENC = 0: encoding angles x given;  1: angles formed in-kernel from (u0, u1, fw, fb) — the frequency layers of
+//   core/models_pt.py:14-68;  2: as 1, and dL/dfw, dL/dfb are reduced over the batch in-kernel (hea_reg.cuh).
+template <typename T, int N, bool GRAD, bool NEED_GX, int ENC, int THREADS>
 __global__ void __launch_bounds__(THREADS) hea_warp_kernel(const HeaParams<T> p, const DepthPack dp) {
+    constexpr bool FREQ_GRAD = GRAD && ENC == 2;
+    constexpr bool WANT_GX = NEED_GX || FREQ_GRAD;
+    static_assert(!(NEED_GX && ENC != 0), "grad_x is only materialised when x is");
     constexpr int NA = 1 << N;
     constexpr int SPW = 32 >> N;
     constexpr int VP = moment_slots(N);
@@ -47,11 +52,12 @@ __global__ void __launch_bounds__(THREADS) hea_warp_kernel(const HeaParams<T> p,
     const int S = p.S, K = p.K, SN = p.S * N, KN = p.K * N;
     Vec4<T>* uc_s = reinterpret_cast<Vec4<T>*>(warp_smem);
     Vec4<T>* rc_s = uc_s + SN;
-    Vec2<T>* sc_all = reinterpret_cast<Vec2<T>*>(uc_s + (NEED_GX ? 2 : 1) * SN);
+    Vec2<T>* sc_all = reinterpret_cast<Vec2<T>*>(uc_s + (WANT_GX ? 2 : 1) * SN);
+    T* uv_all = reinterpret_cast<T*>(sc_all + (size_t)WARPS * SPW * KN);          // FREQ_GRAD only
 
     for (int i = threadIdx.x; i < SN; i += THREADS) {
         uc_s[i] = ldg4(p.ucoef + i);
-        if constexpr (NEED_GX) rc_s[i] = ldg4(p.rcoef + i);
+        if constexpr (WANT_GX) rc_s[i] = ldg4(p.rcoef + i);
     }
 
     const int lane = threadIdx.x & 31;
@@ -83,12 +89,14 @@ __global__ void __launch_bounds__(THREADS) hea_warp_kernel(const HeaParams<T> p,
     }
     const T hd = p.pauli == 0 ? __ldg(p.hdiag + amp) : T(0);
     Vec2<T>* sc = sc_all + (size_t)(warp * SPW + sidx) * KN;   // (sin, cos) of theta/2 per encoding column
+    T* uv = FREQ_GRAD ? uv_all + (size_t)(warp * SPW + sidx) * KN : nullptr;   // source value u of the column
 
     const int64_t gwarp = (int64_t)blockIdx.x * WARPS + warp;
     const int64_t nwarps = (int64_t)gridDim.x * WARPS;
     const int64_t ntiles = (p.B + SPW - 1) / SPW;
     T* mrow = GRAD ? p.mpart + gwarp * p.rowlen : nullptr;
-    T* srow = GRAD ? mrow + (int64_t)S * VP + (int64_t)K * FVP : nullptr;
+    T* frow = GRAD ? mrow + (int64_t)S * VP : nullptr;               // frequency-gradient slots
+    T* srow = GRAD ? frow + (int64_t)K * FVP : nullptr;              // [sum g, sum residual^2]
     __syncthreads();
 
     T re, im, lr, li;
@@ -151,13 +159,25 @@ __global__ void __launch_bounds__(THREADS) hea_warp_kernel(const HeaParams<T> p,
         const bool valid = b < p.B;
         const int64_t bc = valid ? b : p.B - 1;
         __syncwarp();
-        {
+        if constexpr (ENC == 0) {
             const T* xrow = p.x + bc * p.ldx;
 #pragma unroll 4
             for (int c = amp; c < KN; c += NA) {
                 T sn, cs;
                 sincos_half(__ldg(xrow + c), sn, cs);
                 sc[c] = Vec2<T>{sn, cs};
+            }
+        } else {
+            const T* u0row = p.u0 ? p.u0 + bc * p.ldu0 : nullptr;
+            const T* u1row = p.u1 + bc * p.ldu1;
+            const int c0 = p.K0 * N;                       // columns below c0 read source 0
+#pragma unroll 4
+            for (int c = amp; c < KN; c += NA) {
+                const T u = __ldg((c < c0 ? u0row : u1row) + __ldg(p.uidx + c));
+                T sn, cs;
+                sincos_half(fma_(u, __ldg(p.fw + c), p.fb ? __ldg(p.fb + c) : T(0)), sn, cs);
+                sc[c] = Vec2<T>{sn, cs};
+                if constexpr (FREQ_GRAD) uv[c] = u;
             }
         }
         __syncwarp();
@@ -259,7 +279,7 @@ __global__ void __launch_bounds__(THREADS) hea_warp_kernel(const HeaParams<T> p,
             };
             // batch reduction of one sublayer's moments (+ the per-sample dL/dtheta when it opens block k >= 0)
             auto flush = [&](T(&mv)[VP], int s, int k) {
-                if constexpr (NEED_GX && SPW > 1) {
+                if constexpr (WANT_GX && SPW > 1) {
                     if (k >= 0) {   // per-sample: reduce over the sample's own lanes
 #pragma unroll
                         for (int q = 0; q < N; ++q) {
@@ -268,23 +288,37 @@ __global__ void __launch_bounds__(THREADS) hea_warp_kernel(const HeaParams<T> p,
                             for (int m = 1; m < NA; m <<= 1) {
                                 mx += shfl_xor_(mx, m); my += shfl_xor_(my, m); mz += shfl_xor_(mz, m);
                             }
-                            if (amp == q && valid) {
-                                const Vec4<T> r = rc_s[s * N + q];
-                                gxrow[(int64_t)k * N + q] = fma_(r.z, mz, fma_(r.y, my, r.x * mx));
+                            const Vec4<T> r = rc_s[s * N + q];
+                            const T gxv = fma_(r.z, mz, fma_(r.y, my, r.x * mx));
+                            if constexpr (NEED_GX) {
+                                if (amp == q && valid) gxrow[(int64_t)k * N + q] = gxv;
+                            }
+                            if constexpr (FREQ_GRAD) {   // theta = fw*u + fb  =>  d/dfw = gx*u, d/dfb = gx
+                                T fw_ = gxv * uv[k * N + q], fb_ = gxv;      // invalid samples carry g = 0
+#pragma unroll
+                                for (int m = NA; m < 32; m <<= 1) { fw_ += shfl_xor_(fw_, m); fb_ += shfl_xor_(fb_, m); }
+                                if (lane == q) { atomicAdd(frow + k * FVP + 2 * q, fw_); atomicAdd(frow + k * FVP + 2 * q + 1, fb_); }
                             }
                         }
                     }
                 }
                 const T tot = butterfly_reduce<T, VP>(mv, lane);
                 if ((lane & (STR - 1)) == 0) atomicAdd(mrow + (int64_t)s * VP + lane / STR, tot);
-                if constexpr (NEED_GX && SPW == 1) {   // the warp IS the sample: the batch totals are its moments
+                if constexpr (WANT_GX && SPW == 1) {   // the warp IS the sample: the batch totals are its moments
                     if (k >= 0) {
                         const int q3 = (amp < N ? amp : 0) * 3;
                         const T mx = shfl_idx_(tot, q3 * STR), my = shfl_idx_(tot, (q3 + 1) * STR),
                                 mz = shfl_idx_(tot, (q3 + 2) * STR);
-                        if (amp < N && valid) {
+                        if (amp < N) {
                             const Vec4<T> r = rc_s[s * N + amp];
-                            gxrow[(int64_t)k * N + amp] = fma_(r.z, mz, fma_(r.y, my, r.x * mx));
+                            const T gxv = fma_(r.z, mz, fma_(r.y, my, r.x * mx));
+                            if constexpr (NEED_GX) {
+                                if (valid) gxrow[(int64_t)k * N + amp] = gxv;
+                            }
+                            if constexpr (FREQ_GRAD) {
+                                atomicAdd(frow + k * FVP + 2 * amp, gxv * uv[k * N + amp]);
+                                atomicAdd(frow + k * FVP + 2 * amp + 1, gxv);
+                            }
                         }
                     }
                 }

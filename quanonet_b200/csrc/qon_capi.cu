@@ -325,8 +325,8 @@ int make_plan(int64_t B, int n, int K, const int* depth, int dtype, int mode, Pl
         pl->tier = 0;
         pl->nl = n <= max_local ? n : max_local;
         pl->lq = n - pl->nl;
-        // small batches (n <= 5, x given): one amplitude per lane, 2^n lanes per sample — the latency tier
-        if (n <= 5 && !mode_is_enc(mode) && B <= lanes_max_batch()) {
+        // small batches (n <= 5): one amplitude per lane, 2^n lanes per sample — the latency tier
+        if (n <= 5 && B <= lanes_max_batch()) {
             pl->wp = warp_plan(n, K, (int)S, (int)es, mode);
             pl->fast_warp = pl->wp.ok;
         }

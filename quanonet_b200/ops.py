@@ -158,12 +158,6 @@ def latency_tier_max_batch() -> int:
     return int(_lib.load().qon_latency_tier_max_batch())
 
 
-def use_latency_tier(B: int, n: int) -> bool:
-    """True when the x-given entry points would run (B, n) on the latency tier — callers that could also take
-    the fused-encoding entry points (one thread per sample) should then prefer the x-given ones."""
-    return n <= 5 and B <= latency_tier_max_batch()
-
-
 def plan_tier(B: int, n: int, dtype=torch.float32, need_grad=True):
     """(tier, lanes_log2) the library would use: tier 0 register, 1 shared memory, 2 HBM-streamed."""
     import ctypes

@@ -105,11 +105,7 @@ class DataParallelTrainer:
         B = y.shape[0]
         gB = global_batch if global_batch is not None else B * self.world_size
         scale = 2.0 / gB
-        # Small batches take the x-given path: the library then spreads every sample over 2^n lanes (latency
-        # tier, csrc/hea_warp.cuh) — the fused-encoding kernels are one-thread-per-sample.
-        from .ops import use_latency_tier
-        small = use_latency_tier(B, q.n_wires)
-        if self.fused_encoding and not small:
+        if self.fused_encoding:
             return self._compute_grads_fused(inputs, y, scale, gB)
         if self.is_onet:
             branch, trunk = inputs
