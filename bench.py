@@ -316,6 +316,38 @@ def run_b200(args):
     e2e_value = world * B * K / (e2e_ms * 1e-3)
     h2d = sum(t.numel() * t.element_size() for t in host[0])
 
+    # ---- the reference's default batch (utils/common.py:128: 100 samples per step): the latency-bound point
+    #      of SURVEY §8(e).  Eager steps at every N (all-reduce included); CUDA-graph replay of the step at N=1.
+    sB = 100
+    small_model = make_model(dev, seed=0)
+    small_tr = DataParallelTrainer(small_model, lr=1e-3, optimizer="adam", optimizer_kwargs={"capturable": True})
+    sb, st_, sy = synth_batch(sB, seed=300 + rank, device=dev)
+    for _ in range(5):
+        small_tr.step((sb, st_), sy)
+    sync_all()
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s0.record()
+    for _ in range(50):
+        small_tr.step((sb, st_), sy)
+    s1.record()
+    sync_all()
+    small = {"batch_per_gpu": sB, "eager_us_per_step": max_over_ranks(s0.elapsed_time(s1)) / 50 * 1e3}
+    if world == 1:
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            small_tr.step((sb, st_), sy)
+        for _ in range(5):
+            graph.replay()
+        torch.cuda.synchronize()
+        s0.record()
+        for _ in range(200):
+            graph.replay()
+        s1.record()
+        torch.cuda.synchronize()
+        small["graph_us_per_step"] = s0.elapsed_time(s1) / 200 * 1e3
+        small["graph_samples_per_s"] = sB / (small["graph_us_per_step"] * 1e-6)
+        del graph
+
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         sps, ms, Bc, ns = time_cpu_reference(budget_s=20.0)
@@ -358,6 +390,7 @@ def run_b200(args):
                          "frac_of_nominal": achieved / nominal},
             "forward_only": {"value": B / (fwd_ms * 1e-3), "unit": "samples/s",
                              "tflops": f_fwd * B / (fwd_ms * 1e-3) / 1e12},
+            "small_batch": small,
             "final_loss": final_loss,
         }
         if cpu_base is not None:
