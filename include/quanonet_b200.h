@@ -147,6 +147,18 @@ int qon_plan_tier(int64_t B, int n, int dtype, int need_grad, int* lanes_log2);
  * can choose between the x-given and the fused-encoding entry points use it to pick the faster one. */
 int64_t qon_latency_tier_max_batch(void);
 
+/* Exchange step of the data-parallel training step (the reference has no multi-GPU path — main.py:52
+ * pins one GPU — so this replaces the torch.distributed all_reduce a DDP port would add at
+ * solvers/solver_pt.py:235-236): one-shot sum all-reduce of a small fp32 vector over NVLink peer memory, ONE
+ * single-CTA kernel per rank (push to every peer's slot, release/acquire flags, fixed-order sum; see
+ * csrc/qon_peer.cuh).  `peer_bufs` is a HOST array of `world` device pointers to symmetric buffers of
+ * qon_peer_buffer_bytes(max_len, world) bytes each, peer_bufs[rank] being this rank's own; the buffers must be
+ * zero-filled once before first use and every rank must make the same sequence of calls.  src may equal dst.
+ * A peer that does not show up within ~2 s poisons dst with NaN instead of hanging. */
+size_t qon_peer_buffer_bytes(int64_t max_len, int world);
+int qon_peer_allreduce_f32(const float* src, float* dst, int64_t len, void* const* peer_bufs, int world, int rank,
+                           int64_t max_len, void* stream);
+
 /* FP32 FFMA-saturating micro-benchmark (the metric is "% of FP32 peak" and MEASURED_PEAKS.json has
  * no FP32 entry): runs `iters` dependent-chain FFMA rounds on every SM and returns achieved
  * TFLOP/s measured with CUDA events on `stream`; negative on error.  Synchronises the stream. */

@@ -30,6 +30,8 @@ EXPORTED_SYMBOLS = (
     "qon_encoded_mse_step",
     "qon_plan_tier",
     "qon_latency_tier_max_batch",
+    "qon_peer_buffer_bytes",
+    "qon_peer_allreduce_f32",
     "qon_measure_fp32_peak_tflops",
 )
 
@@ -67,6 +69,10 @@ def _declare(lib):
     lib.qon_encoded_mse_step.argtypes = enc_head + [vp, vp, vp, dbl, vp, vp, vp, vp, vp, i64, i32, i32, ip] + ham_tail
     lib.qon_latency_tier_max_batch.restype = i64
     lib.qon_latency_tier_max_batch.argtypes = []
+    lib.qon_peer_buffer_bytes.restype = sz
+    lib.qon_peer_buffer_bytes.argtypes = [i64, i32]
+    lib.qon_peer_allreduce_f32.restype = i32
+    lib.qon_peer_allreduce_f32.argtypes = [vp, vp, i64, c.POINTER(c.c_void_p), i32, i32, i64, vp]
     lib.qon_plan_tier.restype = i32
     lib.qon_plan_tier.argtypes = [i64, i32, i32, i32, ip]
     lib.qon_measure_fp32_peak_tflops.restype = dbl

@@ -11,6 +11,7 @@
 
 #include "../../include/quanonet_b200.h"
 #include "hea_dispatch.cuh"
+#include "qon_peer.cuh"
 
 namespace qon {
 namespace {
@@ -559,6 +560,30 @@ size_t qon_workspace_bytes(int64_t B, int n, int K, const int* depth_per_block, 
 }
 
 int64_t qon_latency_tier_max_batch(void) { return lanes_max_batch(); }
+
+size_t qon_peer_buffer_bytes(int64_t max_len, int world) {
+    if (max_len < 1 || world < 1 || world > kPeerMaxWorld) return 0;
+    return peer_buffer_bytes(max_len, world);
+}
+
+int qon_peer_allreduce_f32(const float* src, float* dst, int64_t len, void* const* peer_bufs, int world, int rank,
+                           int64_t max_len, void* stream) {
+    if (world < 1 || world > kPeerMaxWorld) return fail(QON_ERR_UNSUPPORTED, "world must be in [1, %d] (got %d)", kPeerMaxWorld, world);
+    if (rank < 0 || rank >= world) return fail(QON_ERR_BAD_ARG, "rank %d outside [0, %d)", rank, world);
+    if (len < 0 || len > max_len || max_len > (1 << 20)) return fail(QON_ERR_BAD_ARG, "len (%lld) must be in [0, max_len = %lld <= 2^20]", (long long)len, (long long)max_len);
+    if (!src || !dst || !peer_bufs) return fail(QON_ERR_BAD_ARG, "src, dst and peer_bufs must be non-NULL");
+    PeerPtrs pp{};
+    for (int p = 0; p < world; ++p) {
+        if (!peer_bufs[p] || ((uintptr_t)peer_bufs[p] & 255)) return fail(QON_ERR_BAD_ARG, "peer buffer %d is NULL or not 256-byte aligned", p);
+        pp.p[p] = (char*)peer_bufs[p];
+    }
+    // ~2 s of SM clocks at the nominal 2 GHz (querying cudaDevAttrClockRate costs milliseconds per call)
+    const long long timeout = 4000000000LL;
+    peer_allreduce_kernel<<<1, kPeerThreads, 0, (cudaStream_t)stream>>>(src, dst, (int)len, pp, world, rank, max_len, timeout);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail((int)e, "peer all-reduce launch failed: %s", cudaGetErrorString(e));
+    return 0;
+}
 
 int qon_plan_tier(int64_t B, int n, int dtype, int need_grad, int* lanes_log2) {
     int one = 1;

@@ -278,14 +278,28 @@ def encoded_mse_step(u0: Optional[torch.Tensor], u1: torch.Tensor, fw: torch.Ten
                      need_freq_grad: bool) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
     """``qon_encoded_mse_step``: returns (grad_w (S,3,n), grad_fw (E,) or empty, grad_fb (E,) or empty,
     sums (2,) = [sum g, sum squared residual])."""
-    lib = _lib.load()
-    B = u1.shape[0]
     dt, dev = u1.dtype, u1.device
     E = n_wires * len(depth_per_block)
     grad_w = torch.empty(weights.shape, dtype=dt, device=dev)
     gfw = torch.empty((E,) if need_freq_grad else (0,), dtype=dt, device=dev)
     gfb = torch.empty((E,) if need_freq_grad else (0,), dtype=dt, device=dev)
     sums = torch.empty((2,), dtype=dt, device=dev)
+    encoded_mse_step_into(u0, u1, fw, fb, K0, weights, target, bias, grad_scale, n_wires, depth_per_block, ham_diag,
+                          diag_order, ham_offset, ham_coeff, ham_kind, grad_w, gfw if need_freq_grad else None,
+                          gfb if need_freq_grad else None, sums)
+    return grad_w, gfw, gfb, sums
+
+
+def encoded_mse_step_into(u0, u1, fw, fb, K0, weights, target, bias, grad_scale, n_wires, depth_per_block, ham_diag,
+                          diag_order, ham_offset, ham_coeff, ham_kind, grad_w, grad_fw, grad_fb, sums):
+    """``qon_encoded_mse_step`` writing into caller-owned tensors (e.g. views of the trainer's flat gradient
+    buffer, so a training step needs no copies): grad_w (S,3,n), grad_fw / grad_fb (E,) or None, sums (2,)."""
+    lib = _lib.load()
+    B = u1.shape[0]
+    dt, dev = u1.dtype, u1.device
+    for name, t in (("grad_w", grad_w), ("grad_fw", grad_fw), ("grad_fb", grad_fb), ("sums", sums)):
+        if t is not None and (t.dtype != dt or t.device != dev or not t.is_contiguous()):
+            raise ValueError(f"{name} must be a contiguous {dt} tensor on {dev}")
     with torch.cuda.device(dev):
         head, keep = _enc_args(u0, u1, fw, fb, K0, n_wires, depth_per_block)
         code = _DTYPES[dt]
@@ -299,12 +313,11 @@ def encoded_mse_step(u0: Optional[torch.Tensor], u1: torch.Tensor, fw: torch.Ten
         ws, nbytes = _workspace(B, n_wires, depth, code, True, dev)
         rc = lib.qon_encoded_mse_step(
             *head, wc.data_ptr(), y.data_ptr(), None if bc is None else bc.data_ptr(), float(grad_scale), None,
-            grad_w.data_ptr(), gfw.data_ptr() if need_freq_grad else None, gfb.data_ptr() if need_freq_grad else None,
-            sums.data_ptr(), B, n_wires, len(depth_per_block), depth, None if hd is None else hd.data_ptr(),
-            diag_order, ham_offset, ham_coeff, ham_kind, code, ws.data_ptr(), nbytes,
-            torch.cuda.current_stream(dev).cuda_stream)
+            grad_w.data_ptr(), None if grad_fw is None else grad_fw.data_ptr(),
+            None if grad_fb is None else grad_fb.data_ptr(), sums.data_ptr(), B, n_wires, len(depth_per_block), depth,
+            None if hd is None else hd.data_ptr(), diag_order, ham_offset, ham_coeff, ham_kind, code, ws.data_ptr(),
+            nbytes, torch.cuda.current_stream(dev).cuda_stream)
         _lib.check(rc, "qon_encoded_mse_step")
-    return grad_w, gfw, gfb, sums
 
 
 @encoded_mse_step.register_fake

@@ -68,14 +68,37 @@ class DataParallelTrainer:
         self.kernel_fn = kernel_fn or _default_kernel
         self.is_onet = hasattr(model, "branch_freq")
         self.params = [p for p in model.parameters() if p.requires_grad]
-        # one flat gradient buffer; every p.grad is a view into it -> a single all-reduce per step
-        total = sum(p.numel() for p in self.params)
+        # ONE flat parameter buffer and ONE flat gradient buffer; every p.data / p.grad is a view into them, in
+        # the order the fused kernel writes its outputs: [ansatz | freq weights (circuit order: trunk, branch) |
+        # freq biases | other parameters | model bias | sum of squared residuals | pad].  The kernel then writes
+        # every gradient in place (no copies), the frequency vectors it reads are plain slices (no torch.cat),
+        # and a single all-reduce over the flat buffer is the whole exchange step.
+        q = model.quantum_layer
+        layers = [l for l in ((model.trunk_freq, model.branch_freq) if self.is_onet else (model.freq,))
+                  if isinstance(getattr(l, "weights", None), nn.Parameter)]
+        bias_p = model.bias if isinstance(getattr(model, "bias", None), nn.Parameter) and model.bias.requires_grad else None
+        head = [q.ansatz_weights] + [l.weights for l in layers] + [l.bias for l in layers]
+        head = [p for p in head if p.requires_grad]
+        seen = {id(p) for p in head} | ({id(bias_p)} if bias_p is not None else set())
+        ordered = head + [p for p in self.params if id(p) not in seen] + ([bias_p] if bias_p is not None else [])
+        assert len(ordered) == len(self.params)
+        total = sum(p.numel() for p in ordered)
         p0 = self.params[0]
-        self.flat_grad = torch.zeros(total + 1, dtype=p0.dtype, device=p0.device)   # last slot: sum of squared residuals
+        self.flat_param = torch.cat([p.data.reshape(-1) for p in ordered])
+        self.flat_grad = torch.zeros(total + 2, dtype=p0.dtype, device=p0.device)
         off = 0
-        for p in self.params:
-            p.grad = self.flat_grad[off:off + p.numel()].view_as(p)
-            off += p.numel()
+        for p in ordered:
+            n_el = p.numel()
+            p.data = self.flat_param[off:off + n_el].view_as(p)
+            p.grad = self.flat_grad[off:off + n_el].view_as(p)
+            off += n_el
+        # [sum g (= dL/dbias), sum squared residuals] are adjacent: the kernel's `sums` output lands on them
+        self.sums_off = total - 1 if bias_p is not None else total
+        self.sse_idx = self.sums_off + 1
+        self._freq_span = None
+        if layers and all(l.weights.requires_grad and l.bias.requires_grad for l in layers):
+            nw, ne = q.ansatz_weights.numel(), sum(l.weights.numel() for l in layers)
+            self._freq_span = (nw, ne)            # fw = flat[nw : nw+ne], fb = flat[nw+ne : nw+2ne]
         opt_map = {"adam": torch.optim.Adam, "adamw": torch.optim.AdamW, "sgd": torch.optim.SGD,
                    "rmsprop": torch.optim.RMSprop}       # solvers/solver_pt.py:156-161
         kw = dict(optimizer_kwargs or {})
@@ -85,10 +108,17 @@ class DataParallelTrainer:
         if self.distributed:                               # replicas must start identical
             for p in model.parameters():
                 dist.broadcast(p.data, src=0, group=process_group)
+        # the exchange step: the library's one-kernel NVLink peer-memory all-reduce on CUDA/NCCL groups
+        # (quanonet_b200/comm.py), torch.distributed's all_reduce elsewhere (gloo in the CPU tests)
+        self._all_reduce = None
+        if self.distributed:
+            from .comm import make_all_reduce
+            self._all_reduce = make_all_reduce(self.flat_grad, process_group)
         # whole-model fused kernel (frequency layers evaluated in-kernel, x / grad_x never materialised):
         # needs the register tier with one thread per sample and the standard n-angles-per-block layout
         self.kernel_events = None      # set to a list to collect (start, end) CUDA events around the kernel call
         self.fused_encoding = False
+        self._const_freq = None
         if kernel_fn is None and use_fused_encoding and p0.is_cuda:
             from .ops import encoded_supported
             q = model.quantum_layer
@@ -124,8 +154,7 @@ class DataParallelTrainer:
         self._event_end(ev)
         self.flat_grad.zero_()
         q.ansatz_weights.grad.copy_(gw)
-        if bias is not None:
-            m.bias.grad.copy_(g.sum().reshape(1))
+        self.flat_grad[self.sums_off] = g.sum()      # dL/dbias when the model has a bias (same slot), else a spare
         if need_gx:
             if self.is_onet:
                 et = m.trunk_enc_size
@@ -137,10 +166,10 @@ class DataParallelTrainer:
                 gw_f, gb_f = _freq_grads(m.freq, u, gx)
                 m.freq.weights.grad.copy_(gw_f)
                 m.freq.bias.grad.copy_(gb_f)
-        self.flat_grad[-1] = (g * g).sum() / (scale * scale)          # sum of squared residuals on this shard
+        self.flat_grad[self.sse_idx] = (g * g).sum() / (scale * scale)   # sum of squared residuals on this shard
         if self.distributed and self.world_size > 1:
-            dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM, group=self.group)
-        return self.flat_grad[-1] / gB
+            self._all_reduce(self.flat_grad)
+        return self.flat_grad[self.sse_idx] / gB
 
     def _event_start(self):
         if self.kernel_events is None:
@@ -166,11 +195,22 @@ class DataParallelTrainer:
         return fw, None
 
     def _compute_grads_fused(self, inputs, y, scale, gB):
-        from .ops import encoded_mse_step
+        from .ops import encoded_mse_step_into
         m = self.model
         q = m.quantum_layer
         depths = [d for _, d in q.block_configs]
-        fw, fb = self._freq_vectors()
+        tf = bool(m.if_trainable_freq)
+        fg = self.flat_grad
+        if tf and self._freq_span is not None:
+            nw, ne = self._freq_span
+            fw, fb = self.flat_param[nw:nw + ne], self.flat_param[nw + ne:nw + 2 * ne]
+            gfw, gfb = fg[nw:nw + ne], fg[nw + ne:nw + 2 * ne]
+        else:
+            if self._const_freq is None:
+                self._const_freq = self._freq_vectors()
+            (fw, fb), gfw, gfb = self._const_freq, None, None
+            if tf:
+                raise NotImplementedError("frozen frequency-layer parameters are not supported by the fused step")
         if self.is_onet:
             branch, trunk = inputs
             u0, u1, K0 = trunk, branch, m.trunk_enc_size // q.n_wires
@@ -178,29 +218,18 @@ class DataParallelTrainer:
             (u1,) = inputs
             u0, K0 = None, 0
         bias = m.bias if hasattr(m, "bias") else None
-        tf = bool(m.if_trainable_freq)
         if q.use_full_ham:
             ham = (q.ham_diag.to(device=u1.device, dtype=fw.dtype), _DIAG_ORDER[q.diag_order], 0.0, 0.0, _lib.QON_HAM_DIAG)
         else:
             ham = (None, _lib.QON_DIAG_LSB0, q.ham_offset, q.ham_coeff, _PAULI_KIND[q.ham_pauli])
         ev = self._event_start()
-        gw, gfw, gfb, sums = encoded_mse_step(u0, u1, fw, fb, K0, q.ansatz_weights, y.reshape(-1), bias, scale,
-                                              q.n_wires, depths, *ham, tf)
+        # every output is a view of the flat gradient buffer: grad_w, grad_fw, grad_fb, [dL/dbias, sum sq. residuals]
+        encoded_mse_step_into(u0, u1, fw, fb, K0, q.ansatz_weights.data, y.reshape(-1), bias, scale, q.n_wires, depths,
+                              *ham, q.ansatz_weights.grad, gfw, gfb, fg[self.sums_off:self.sums_off + 2])
         self._event_end(ev)
-        self.flat_grad.zero_()
-        q.ansatz_weights.grad.copy_(gw)
-        if bias is not None:
-            m.bias.grad.copy_(sums[0:1])
-        if tf:
-            off = 0
-            for layer in ((m.trunk_freq, m.branch_freq) if self.is_onet else (m.freq,)):
-                layer.weights.grad.copy_(gfw[off:off + layer.out_features])
-                layer.bias.grad.copy_(gfb[off:off + layer.out_features])
-                off += layer.out_features
-        self.flat_grad[-1] = sums[1]
         if self.distributed and self.world_size > 1:
-            dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM, group=self.group)
-        return self.flat_grad[-1] / gB
+            self._all_reduce(fg)
+        return fg[self.sse_idx] / gB
 
     def step(self, inputs, y, global_batch=None):
         loss = self.compute_grads(inputs, y, global_batch)
