@@ -596,3 +596,17 @@ def test_latency_tier_all_widths(cuda_device):
                 e, gx, gw = hea_expval_backward(gt, xt, wt, n, depths, hdt, 0, off, co, kind, True)
                 errs = (rel_l2(e.cpu().numpy()[:, 0], e_ref), rel_l2(gx.cpu().numpy(), gx_ref), rel_l2(gw.cpu().numpy(), gw_ref))
                 assert max(errs) < tol, (n, kind, dtype, errs)
+
+
+def test_peer_allreduce_single_rank(cuda_device):
+    """The exchange-step kernel (csrc/qon_peer.cuh) through torch's symmetric memory on a one-rank NCCL group:
+    the degenerate all-reduce must return its input, survive CUDA-graph replay, and never report a timeout.
+    (World sizes 2 and 8 are checked by scripts/peer_allreduce_check.py on multi-GPU boxes; the sharding logic
+    by tests/test_dp_gloo.py.)"""
+    import subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "1",
+                        "--master-addr", "127.0.0.1", "--master-port", "29577",
+                        os.path.join(root, "scripts", "peer_allreduce_check.py"), "50"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "iterations equal" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
