@@ -70,11 +70,18 @@ def make_all_reduce(flat: torch.Tensor, group=None) -> Callable[[torch.Tensor], 
         return nccl
     if dist.get_backend(group) != "nccl" or dist.get_world_size(group) > 8:
         return nccl
+    peer, err = None, None
     try:
-        return PeerAllReduce(flat.numel(), flat.device, group)
-    except Exception as exc:    # symmetric memory unavailable (no P2P, older driver ...): NCCL does the exchange
-        if choice == "peer":
-            raise
-        import warnings
-        warnings.warn(f"peer-memory all-reduce unavailable ({exc}); using NCCL")
-        return nccl
+        peer = PeerAllReduce(flat.numel(), flat.device, group)
+    except Exception as exc:    # symmetric memory unavailable (no P2P, older driver ...)
+        err = exc
+    # every rank must take the same path: agree on the outcome before anyone uses it
+    ok = torch.tensor([1 if peer is not None else 0], device=flat.device, dtype=torch.int32)
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+    if int(ok.item()) == 1:
+        return peer
+    if choice == "peer":
+        raise RuntimeError(f"peer-memory all-reduce unavailable on at least one rank ({err})")
+    import warnings
+    warnings.warn(f"peer-memory all-reduce unavailable on at least one rank ({err}); NCCL does the exchange")
+    return nccl
