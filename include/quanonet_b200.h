@@ -159,6 +159,21 @@ size_t qon_peer_buffer_bytes(int64_t max_len, int world);
 int qon_peer_allreduce_f32(const float* src, float* dst, int64_t len, void* const* peer_bufs, int world, int rank,
                            int64_t max_len, void* stream);
 
+/* qon_encoded_mse_step for data-parallel training (fp32): compute step and exchange step in one pass.  The finalize
+ * kernel pushes every gradient into the peers' slots of the symmetric buffers as it is produced, the last CTA
+ * signals / waits / sums in rank order, and the all-reduced gradient of every parameter lands in `flat`:
+ *   flat[w_off ...]    (S,3,n) ansatz gradient          flat[fw_off ...], flat[fb_off ...]  (n*K,) each, or both -1
+ *   flat[sums_off ..]  [sum g (= dL/dbias), sum of squared residuals]        every other index of flat: 0
+ * peer_bufs / world / rank / max_len as in qon_peer_allreduce_f32 (same buffers, same protocol: the two calls may be
+ * mixed on one buffer as long as every rank makes the same sequence). */
+int qon_encoded_mse_step_dp(const void* u0, int64_t ldu0, int in0, int K0, const void* u1, int64_t ldu1, int in1,
+                            const void* fw, const void* fb, const void* w, const void* target, const void* bias,
+                            double grad_scale, void* out, float* flat, int64_t flat_len, int64_t w_off, int64_t fw_off,
+                            int64_t fb_off, int64_t sums_off, void* const* peer_bufs, int world, int rank,
+                            int64_t max_len, int64_t B, int n, int K, const int* depth_per_block, const void* ham_diag,
+                            int diag_order, double ham_offset, double ham_coeff, int ham_kind, void* workspace,
+                            size_t workspace_bytes, void* stream);
+
 /* FP32 FFMA-saturating micro-benchmark (the metric is "% of FP32 peak" and MEASURED_PEAKS.json has
  * no FP32 entry): runs `iters` dependent-chain FFMA rounds on every SM and returns achieved
  * TFLOP/s measured with CUDA events on `stream`; negative on error.  Synchronises the stream. */

@@ -32,6 +32,7 @@ EXPORTED_SYMBOLS = (
     "qon_latency_tier_max_batch",
     "qon_peer_buffer_bytes",
     "qon_peer_allreduce_f32",
+    "qon_encoded_mse_step_dp",
     "qon_measure_fp32_peak_tflops",
 )
 
@@ -73,6 +74,10 @@ def _declare(lib):
     lib.qon_peer_buffer_bytes.argtypes = [i64, i32]
     lib.qon_peer_allreduce_f32.restype = i32
     lib.qon_peer_allreduce_f32.argtypes = [vp, vp, i64, c.POINTER(c.c_void_p), i32, i32, i64, vp]
+    lib.qon_encoded_mse_step_dp.restype = i32
+    lib.qon_encoded_mse_step_dp.argtypes = [vp, i64, i32, i32, vp, i64, i32, vp, vp, vp, vp, vp, dbl, vp,
+                                            vp, i64, i64, i64, i64, i64, c.POINTER(c.c_void_p), i32, i32, i64,
+                                            i64, i32, i32, ip, vp, i32, dbl, dbl, i32, vp, sz, vp]
     lib.qon_plan_tier.restype = i32
     lib.qon_plan_tier.argtypes = [i64, i32, i32, i32, ip]
     lib.qon_measure_fp32_peak_tflops.restype = dbl

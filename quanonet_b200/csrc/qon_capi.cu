@@ -164,6 +164,123 @@ __global__ void finalize_enc_kernel(const T* __restrict__ mpart, int rows, int64
 }
 
 // ---------------------------------------------------------------------------------------------
+// finalize + exchange in ONE kernel (data-parallel training, fp32): the work of finalize_kernel and
+// finalize_enc_kernel, with every gradient pushed straight into the peers' slots of the symmetric buffers as
+// it is produced (qon_peer.cuh protocol), then the last CTA to finish signals the peers, waits for theirs and
+// writes the rank-ordered sum into the flat gradient buffer.  grid = S + K + 1 CTAs:
+//   CTA s < S      : the 3n angle gradients of sublayer s      -> flat[w_off + s*3n ...]
+//   CTA S + k      : dL/dfw, dL/dfb of encoding block k         -> flat[fw_off + k*n ...], flat[fb_off + k*n ...]
+//   CTA S + K      : [sum g, sum residual^2] -> flat[sums_off ...]; zeros for every other index of the buffer
+// ---------------------------------------------------------------------------------------------
+struct FlatLayout { int64_t w_off, fw_off, fb_off, sums_off, len; };
+
+__global__ void __launch_bounds__(256) finalize_exchange_kernel(const float* __restrict__ mpart, int rows, int64_t rowlen,
+                                                                int VP, int FVP, int n, int S, int K,
+                                                                const float* __restrict__ w, float* flat, FlatLayout fl,
+                                                                PeerPtrs pp, int world, int rank, int64_t max_len,
+                                                                long long timeout_cycles) {
+    __shared__ double sm[256];
+    __shared__ int s_last, s_timeout;
+    const int t = threadIdx.x, b = blockIdx.x;
+    char* mine = pp.p[rank];
+    unsigned* my_flags = reinterpret_cast<unsigned*>(mine);
+    unsigned* epoch_ctr = reinterpret_cast<unsigned*>(mine + 128);
+    unsigned* err_word = reinterpret_cast<unsigned*>(mine + 132);
+    unsigned* done_ctr = reinterpret_cast<unsigned*>(mine + 136);
+    const unsigned e = *epoch_ctr + 1u;              // only the last CTA of a launch advances it
+    const size_t set_off = (size_t)(e & 1u) * world * (size_t)max_len;
+    auto push = [&](int64_t idx, float v) {
+        for (int p = 0; p < world; ++p)
+            (reinterpret_cast<float*>(pp.p[p] + kPeerHeaderBytes) + set_off + (size_t)rank * max_len)[idx] = v;
+    };
+
+    if (b < S) {
+        const int RG = 256 / VP, slot = t % VP, rg = t / VP;
+        double acc = 0.0;
+        if (rg < RG)
+            for (int r = rg; r < rows; r += RG) acc += (double)mpart[(int64_t)r * rowlen + (int64_t)b * VP + slot];
+        sm[t] = rg < RG ? acc : 0.0;
+        __syncthreads();
+        if (t < n) {
+            double m[3];
+            for (int v = 0; v < 3; ++v) {
+                double a2 = 0.0;
+                for (int g = 0; g < RG; ++g) a2 += sm[g * VP + 3 * t + v];
+                m[v] = a2;
+            }
+            const double bb = (double)w[((int64_t)b * 3 + 1) * n + t];
+            const double cc = (double)w[((int64_t)b * 3 + 2) * n + t];
+            double Sb, Cb, Sc, Cc;
+            sincos(bb, &Sb, &Cb);
+            sincos(cc, &Sc, &Cc);
+            const int64_t base = fl.w_off + (int64_t)b * 3 * n + t;
+            push(base, (float)(Cb * m[1] - Sb * (Cc * m[0] - Sc * m[2])));
+            push(base + n, (float)(Cc * m[2] + Sc * m[0]));
+            push(base + 2 * n, (float)m[1]);
+        }
+    } else {
+        const int k = b - S;
+        const int width = k < K ? FVP : 2;
+        const int64_t base = (int64_t)S * VP + (k < K ? (int64_t)k * FVP : (int64_t)K * FVP);
+        const int RG = 256 / width, slot = t % width, rg = t / width;
+        double acc = 0.0;
+        if (rg < RG)
+            for (int r = rg; r < rows; r += RG) acc += (double)mpart[(int64_t)r * rowlen + base + slot];
+        sm[t] = rg < RG ? acc : 0.0;
+        __syncthreads();
+        if (t < width) {
+            double tot = 0.0;
+            for (int g = 0; g < RG; ++g) tot += sm[g * width + t];
+            if (k < K) {
+                const int q = t >> 1;
+                if (q < n && fl.fw_off >= 0) push(((t & 1) ? fl.fb_off : fl.fw_off) + (int64_t)k * n + q, (float)tot);
+            } else {
+                push(fl.sums_off + t, (float)tot);
+            }
+        }
+        if (k == K) {      // indices no CTA produces (other parameters, padding) must not carry stale slot contents
+            const int64_t nw = (int64_t)3 * n * S, ne = (int64_t)n * K;
+            for (int64_t i = t; i < fl.len; i += 256) {
+                const bool covered = (i >= fl.w_off && i < fl.w_off + nw) || (i >= fl.sums_off && i < fl.sums_off + 2) ||
+                                     (fl.fw_off >= 0 && ((i >= fl.fw_off && i < fl.fw_off + ne) ||
+                                                         (i >= fl.fb_off && i < fl.fb_off + ne)));
+                if (!covered) push(i, 0.f);
+            }
+        }
+    }
+    // last CTA of this rank: exchange
+    __threadfence_system();
+    __syncthreads();
+    if (t == 0) {
+        s_timeout = 0;
+        s_last = atomicAdd(done_ctr, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    if (t == 0) *done_ctr = 0u;
+    if (t < world) st_release_sys(reinterpret_cast<unsigned*>(pp.p[t]) + rank, e);
+    if (t < world) {
+        const long long t0 = clock64();
+        while ((int)(ld_acquire_sys(my_flags + t) - e) < 0) {
+            if (clock64() - t0 > timeout_cycles) { s_timeout = 1; break; }
+        }
+    }
+    __syncthreads();
+    const bool bad = s_timeout != 0;
+    const float* slots = reinterpret_cast<const float*>(mine + kPeerHeaderBytes) + set_off;
+    for (int64_t i = t; i < fl.len; i += 256) {
+        float acc = 0.f;
+        for (int p = 0; p < world; ++p) acc += __ldcg(slots + (size_t)p * max_len + i);
+        flat[i] = bad ? __int_as_float(0x7fc00000) : acc;
+    }
+    if (t == 0) {
+        *epoch_ctr = e;
+        if (bad) *err_word = e;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // FP32 FFMA peak probe
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) ffma_peak_kernel(float* out, int iters, float y, float z) {
@@ -404,6 +521,8 @@ struct Job {
     bool grad = false;
     const void *grad_out = nullptr, *target = nullptr, *bias = nullptr; double gscale = 0; void* gbuf = nullptr;
     void* grad_x = nullptr; int64_t ldgx = 0; void* grad_w = nullptr;
+    // data-parallel exchange fused into finalize (fp32, fused-encoding training step)
+    float* flat = nullptr; FlatLayout fl{}; PeerPtrs peers{}; int world = 0, rank = 0; int64_t peer_max_len = 0;
 };
 
 int job_mode(const Job& j) {
@@ -428,7 +547,7 @@ int run(const Job& j) {
         if (j.K0 < K && (!j.u1 || j.in1 < 1 || j.ldu1 < j.in1)) return fail(QON_ERR_BAD_ARG, "bad source 1 (u1/in1/ldu1)");
         if (!j.grad && !j.out) return fail(QON_ERR_BAD_ARG, "out must be non-NULL");
     }
-    if (j.grad && !j.grad_w) return fail(QON_ERR_BAD_ARG, "grad_w must be non-NULL");
+    if (j.grad && !j.grad_w && !j.flat) return fail(QON_ERR_BAD_ARG, "grad_w must be non-NULL");
     if (j.grad && !j.grad_out && !j.target) return fail(QON_ERR_BAD_ARG, "grad_out (or target) must be non-NULL");
     if (j.grad_x && j.ldgx < (int64_t)n * K)
         return fail(QON_ERR_BAD_ARG, "ldgx (%lld) < n*K (%d)", (long long)j.ldgx, n * K);
@@ -498,6 +617,17 @@ int run(const Job& j) {
                 e = generic_launch_f64(n, mode, pl.grid, pl.gp, (const HeaParams<double>&)p, pl.vp, (double*)gstate, st);
         }
         if (e != cudaSuccess) return fail((int)e, "kernel launch failed: %s", cudaGetErrorString(e));
+    }
+    if (j.grad && j.flat) {
+        if constexpr (sizeof(T) == 4) {
+            const int rows = j.B > 0 ? pl.rows : 0;
+            finalize_exchange_kernel<<<pl.S + K + 1, 256, 0, st>>>(
+                (const float*)p.mpart, rows, pl.rowlen, pl.vp, pl.fvp, n, pl.S, K, (const float*)j.w, j.flat, j.fl, j.peers,
+                j.world, j.rank, j.peer_max_len, 4000000000LL);
+            cudaError_t e = cudaGetLastError();
+            if (e != cudaSuccess) return fail((int)e, "finalize+exchange launch failed: %s", cudaGetErrorString(e));
+        }
+        return 0;
     }
     if (j.grad) {
         const int rows = j.B > 0 ? pl.rows : 0;
@@ -657,6 +787,45 @@ int qon_encoded_mse_step(const void* u0, int64_t ldu0, int in0, int K0, const vo
     j.enc = true; j.u0 = u0; j.ldu0 = ldu0; j.in0 = in0; j.K0 = K0; j.u1 = u1; j.ldu1 = ldu1; j.in1 = in1;
     j.fw = fw; j.fb = fb; j.grad = true; j.target = target; j.bias = bias; j.gscale = grad_scale;
     j.grad_w = grad_w; j.grad_fw = grad_fw; j.grad_fb = grad_fb; j.sums = sums;
+    return dispatch(j);
+}
+
+int qon_encoded_mse_step_dp(const void* u0, int64_t ldu0, int in0, int K0, const void* u1, int64_t ldu1, int in1,
+                            const void* fw, const void* fb, const void* w, const void* target, const void* bias,
+                            double grad_scale, void* out, float* flat, int64_t flat_len, int64_t w_off, int64_t fw_off,
+                            int64_t fb_off, int64_t sums_off, void* const* peer_bufs, int world, int rank,
+                            int64_t max_len, int64_t B, int n, int K, const int* depth_per_block, const void* ham_diag,
+                            int diag_order, double ham_offset, double ham_coeff, int ham_kind, void* workspace,
+                            size_t workspace_bytes, void* stream) {
+    if (!target) return fail(QON_ERR_BAD_ARG, "target must be non-NULL");
+    if (!flat || !peer_bufs) return fail(QON_ERR_BAD_ARG, "flat and peer_bufs must be non-NULL");
+    if (world < 1 || world > kPeerMaxWorld) return fail(QON_ERR_UNSUPPORTED, "world must be in [1, %d] (got %d)", kPeerMaxWorld, world);
+    if (rank < 0 || rank >= world) return fail(QON_ERR_BAD_ARG, "rank %d outside [0, %d)", rank, world);
+    if (flat_len < 1 || flat_len > max_len) return fail(QON_ERR_BAD_ARG, "flat_len (%lld) must be in [1, max_len = %lld]", (long long)flat_len, (long long)max_len);
+    if (n < 1 || K < 1 || !depth_per_block) return fail(QON_ERR_BAD_ARG, "bad circuit description");
+    int64_t S = 0;
+    for (int k = 0; k < K; ++k) S += depth_per_block[k];
+    const int64_t nw = 3 * (int64_t)n * S, ne = (int64_t)n * K;
+    const bool freq = fw_off >= 0 || fb_off >= 0;
+    if (w_off < 0 || w_off + nw > flat_len || sums_off < 0 || sums_off + 2 > flat_len ||
+        (freq && (fw_off < 0 || fb_off < 0 || fw_off + ne > flat_len || fb_off + ne > flat_len)))
+        return fail(QON_ERR_BAD_ARG, "gradient offsets fall outside the flat buffer");
+    Job j;
+    fill_common(j, w, out, B, n, K, depth_per_block, ham_diag, diag_order, ham_offset, ham_coeff, ham_kind, QON_F32,
+                workspace, workspace_bytes, stream);
+    j.enc = true; j.u0 = u0; j.ldu0 = ldu0; j.in0 = in0; j.K0 = K0; j.u1 = u1; j.ldu1 = ldu1; j.in1 = in1;
+    j.fw = fw; j.fb = fb; j.grad = true; j.target = target; j.bias = bias; j.gscale = grad_scale;
+    // grad_fw / grad_fb only select the kernel variant (frequency gradients reduced in-kernel); nothing is written
+    // through them: the fused finalize pushes every gradient into the peers' slots and then into `flat`
+    j.grad_fw = freq ? (void*)(flat + fw_off) : nullptr;
+    j.grad_fb = freq ? (void*)(flat + fb_off) : nullptr;
+    j.flat = flat;
+    j.fl = FlatLayout{w_off, freq ? fw_off : -1, freq ? fb_off : -1, sums_off, flat_len};
+    for (int p = 0; p < world; ++p) {
+        if (!peer_bufs[p] || ((uintptr_t)peer_bufs[p] & 255)) return fail(QON_ERR_BAD_ARG, "peer buffer %d is NULL or not 256-byte aligned", p);
+        j.peers.p[p] = (char*)peer_bufs[p];
+    }
+    j.world = world; j.rank = rank; j.peer_max_len = max_len;
     return dispatch(j);
 }
 

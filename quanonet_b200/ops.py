@@ -320,6 +320,38 @@ def encoded_mse_step_into(u0, u1, fw, fb, K0, weights, target, bias, grad_scale,
         _lib.check(rc, "qon_encoded_mse_step")
 
 
+def encoded_mse_step_dp(u0, u1, fw, fb, K0, weights, target, bias, grad_scale, n_wires, depth_per_block, ham_diag,
+                        diag_order, ham_offset, ham_coeff, ham_kind, flat, w_off, fw_off, fb_off, sums_off, peer):
+    """``qon_encoded_mse_step_dp``: the training step's gradient AND its all-reduce over the ranks in one pass —
+    the finalize kernel pushes every gradient into the peers' symmetric buffers and the summed result lands in
+    ``flat`` (fp32).  ``peer`` is a ``quanonet_b200.comm.PeerAllReduce``; ``fw_off = fb_off = -1`` for fixed
+    frequency layers."""
+    lib = _lib.load()
+    B = u1.shape[0]
+    dt, dev = u1.dtype, u1.device
+    if dt != torch.float32 or flat.dtype != torch.float32 or not flat.is_contiguous() or flat.device != dev:
+        raise ValueError("the fused exchange takes float32 inputs and a contiguous float32 flat buffer on the same device")
+    if flat.numel() > peer.max_len:
+        raise ValueError(f"flat buffer ({flat.numel()}) exceeds the peer buffers' max_len ({peer.max_len})")
+    with torch.cuda.device(dev):
+        head, keep = _enc_args(u0, u1, fw, fb, K0, n_wires, depth_per_block)
+        wc = weights.to(dt).contiguous()
+        y = target.to(dt).reshape(-1).contiguous()
+        if y.numel() != B:
+            raise ValueError(f"target must have B = {B} elements, got {y.numel()}")
+        bc = None if bias is None else bias.to(dt).reshape(-1).contiguous()
+        hd = None if ham_diag is None else ham_diag.to(dtype=dt, device=dev).contiguous()
+        depth = _lib.int_array(depth_per_block)
+        ws, nbytes = _workspace(B, n_wires, depth, _DTYPES[dt], True, dev)
+        rc = lib.qon_encoded_mse_step_dp(
+            *head, wc.data_ptr(), y.data_ptr(), None if bc is None else bc.data_ptr(), float(grad_scale), None,
+            flat.data_ptr(), flat.numel(), int(w_off), int(fw_off), int(fb_off), int(sums_off), peer.ptrs, peer.world,
+            peer.rank, peer.max_len, B, n_wires, len(depth_per_block), depth, None if hd is None else hd.data_ptr(),
+            diag_order, ham_offset, ham_coeff, ham_kind, ws.data_ptr(), nbytes,
+            torch.cuda.current_stream(dev).cuda_stream)
+        _lib.check(rc, "qon_encoded_mse_step_dp")
+
+
 @encoded_mse_step.register_fake
 def _(u0, u1, fw, fb, K0, weights, target, bias, grad_scale, n_wires, depth_per_block, ham_diag, diag_order,
       ham_offset, ham_coeff, ham_kind, need_freq_grad):

@@ -124,6 +124,12 @@ class DataParallelTrainer:
             q = model.quantum_layer
             standard = all(e == q.n_wires and d >= 1 for e, d in q.block_configs)
             self.fused_encoding = standard and encoded_supported(q.n_wires, p0.dtype)
+        # with the peer-memory exchange available, the fused step also does the all-reduce (one finalize kernel)
+        from .comm import PeerAllReduce
+        self._fused_exchange = (self.fused_encoding and self.world_size > 1 and p0.dtype == torch.float32
+                                and isinstance(self._all_reduce, PeerAllReduce)
+                                and (self._freq_span is not None or not getattr(model, "if_trainable_freq", False))
+                                and q.ansatz_weights.requires_grad)
 
     # -- one step -------------------------------------------------------------------------------
     @torch.no_grad()
@@ -222,6 +228,18 @@ class DataParallelTrainer:
             ham = (q.ham_diag.to(device=u1.device, dtype=fw.dtype), _DIAG_ORDER[q.diag_order], 0.0, 0.0, _lib.QON_HAM_DIAG)
         else:
             ham = (None, _lib.QON_DIAG_LSB0, q.ham_offset, q.ham_coeff, _PAULI_KIND[q.ham_pauli])
+        if self._fused_exchange:
+            # compute step + exchange step in one pass: the finalize kernel pushes the gradients to the peers and
+            # leaves the all-reduced flat gradient in fg (quanonet_b200/comm.py, csrc/qon_capi.cu)
+            from .ops import encoded_mse_step_dp
+            ev = self._event_start()
+            nw = q.ansatz_weights.numel()
+            ne = self._freq_span[1] if gfw is not None else 0
+            encoded_mse_step_dp(u0, u1, fw, fb, K0, q.ansatz_weights.data, y.reshape(-1), bias, scale, q.n_wires, depths,
+                                *ham, fg, 0, nw if gfw is not None else -1, nw + ne if gfw is not None else -1,
+                                self.sums_off, self._all_reduce)
+            self._event_end(ev)
+            return fg[self.sse_idx] / gB
         ev = self._event_start()
         # every output is a view of the flat gradient buffer: grad_w, grad_fw, grad_fb, [dL/dbias, sum sq. residuals]
         encoded_mse_step_into(u0, u1, fw, fb, K0, q.ansatz_weights.data, y.reshape(-1), bias, scale, q.n_wires, depths,
