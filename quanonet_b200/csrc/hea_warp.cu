@@ -1,7 +1,7 @@
 // Small-batch latency tier: instantiations, planning and launch (fp32 and fp64, n = 1..5, modes 0..5 as in
 // hea_reg_inst.cuh).
 #include "hea_dispatch.cuh"
-#include "hea_warp.cuh"
+#include "hea_warp_wide.cuh"
 
 namespace qon {
 
@@ -22,8 +22,28 @@ WarpKern<T> warp_kernel_n(int mode) {
     }
 }
 
+template <int N>
+WarpKern<float> warp_wide_kernel_n(int mode) {
+    switch (mode) {
+        case 0: return hea_warp_wide_kernel<N, false, false, kWarpThreads>;
+        case 1: return hea_warp_wide_kernel<N, true, true, kWarpThreads>;
+        case 2: return hea_warp_wide_kernel<N, true, false, kWarpThreads>;
+        default: return nullptr;
+    }
+}
+
 template <typename T>
 WarpKern<T> warp_kernel(int n, int mode) {
+    if constexpr (sizeof(T) == 4) {     // n = 6..10: several amplitudes per lane (hea_warp_wide.cuh), fp32, x given
+        switch (n) {
+            case 6: return warp_wide_kernel_n<6>(mode);
+            case 7: return warp_wide_kernel_n<7>(mode);
+            case 8: return warp_wide_kernel_n<8>(mode);
+            case 9: return warp_wide_kernel_n<9>(mode);
+            case 10: return warp_wide_kernel_n<10>(mode);
+            default: break;
+        }
+    }
     switch (n) {
         case 1: return warp_kernel_n<T, 1>(mode);
         case 2: return warp_kernel_n<T, 2>(mode);

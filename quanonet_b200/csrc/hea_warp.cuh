@@ -30,7 +30,8 @@ template <typename T>
 __host__ __device__ inline size_t warp_smem_bytes(int n, int K, int S, bool want_gx, bool freq_grad, int threads) {
     const size_t tbl = (size_t)S * n * sizeof(Vec4<T>) * (want_gx ? 2 : 1);
     const size_t per_sample = (size_t)K * n * (freq_grad ? 3 : 2) * sizeof(T);   // (sin, cos) [+ source value u]
-    return tbl + (size_t)(threads / 32) * (32 >> n) * per_sample;
+    const int spw = n >= 5 ? 1 : (32 >> n);                                          // samples per warp
+    return tbl + (size_t)(threads / 32) * spw * per_sample;
 }
 
 //   ENC = 0: encoding angles x given;  1: angles formed in-kernel from (u0, u1, fw, fb) — the frequency layers of

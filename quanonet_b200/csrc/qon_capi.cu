@@ -355,6 +355,18 @@ int64_t lanes_max_batch() {
     return v;
 }
 
+// Largest batch the wide latency tier (n = 6..10, hea_warp_wide.cuh) serves; above it the shared-memory tier's
+// throughput wins.  QON_WIDE_MAX_B overrides every entry (0 disables).
+int64_t wide_max_batch(int n) {
+    static const int64_t ov = [] { const char* e = getenv("QON_WIDE_MAX_B"); return e ? (int64_t)atoll(e) : (int64_t)-1; }();
+    if (ov >= 0) return ov;
+    // measured against the shared-memory tier (fwd+grad, 60 sublayers; scripts/small_batch_widths.py): n = 6: 103 us vs
+    // 785 us at B = 100, level at ~8,000; n = 8: 171 vs 934 us, level at ~4,000; n = 9: 480 vs 1,033 us, level at
+    // ~1,500; n = 10 (32 amplitudes per lane, 255 registers): 1,215 vs 1,110 us — not used
+    static const int64_t tbl[5] = {8192, 4096, 2048, 1024, 0};      // n = 6..10
+    return n >= 6 && n <= 10 ? tbl[n - 6] : 0;
+}
+
 // QON_HBM_TIER=generic falls back to the one-CTA-per-sample kernel for n >= 14 (experiments / A-B tests)
 bool hbm_disabled() {
     static const bool v = [] {
@@ -414,7 +426,25 @@ int make_plan(int64_t B, int n, int K, const int* depth, int dtype, int mode, Pl
     pl->fast_smem = false;
     pl->fast_hbm = false;
     pl->fast_warp = false;
-    if (dtype == QON_F32 && !mode_is_enc(mode) && n >= smem_first_n(grad) && n <= kSmemMaxN) {
+    if (dtype == QON_F32 && !mode_is_enc(mode) && n >= 6 && n <= 10 && B <= wide_max_batch(n)) {
+        pl->wp = warp_plan(n, K, (int)S, (int)es, mode);
+        pl->fast_warp = pl->wp.ok;
+    }
+    if (pl->fast_warp) {
+        // wide latency tier: one warp per sample, 2^(n-5) amplitudes per lane
+        pl->tier = 0;
+        pl->nl = n - 5;
+        pl->lq = 5;
+        const int warps = pl->wp.threads / 32;
+        int64_t grid = (B + warps - 1) / warps;
+        const int64_t cap = (int64_t)di.sms * pl->wp.blocks_per_sm;
+        if (grid > cap) grid = cap;
+        if (grid < 1) grid = 1;
+        pl->grid = (int)grid;
+        pl->rows = (int)grid * warps;
+        pl->vp = moment_slots(n);
+        pl->fvp = freq_slots(n);
+    } else if (dtype == QON_F32 && !mode_is_enc(mode) && n >= smem_first_n(grad) && n <= kSmemMaxN) {
         // fp32 shared-memory tier: register-blocked FFMA2 passes over a state held in shared memory
         pl->sp = smem_plan(n, mode);
         if (!pl->sp.ok) return fail(QON_ERR_UNSUPPORTED, "shared-memory tier kernel does not fit for n=%d", n);

@@ -252,7 +252,9 @@ def test_edge_cases(cuda_device):
 
 @pytest.mark.parametrize("n", [6, 7, 8, 9, 10, 11, 12, 13])
 def test_larger_qubit_counts(cuda_device, n):
-    """Lane-distributed register tier (n = 6..10) and the shared-memory tier (n >= 11) vs the oracle."""
+    """n = 6..13 vs the oracle: at this batch size fp32 runs on the wide latency tier (n <= 10) or the
+    shared-memory tier (n >= 11; n <= 10 too in test_throughput_tier_on_small_batches), fp64 on the lane-distributed
+    register tier / generic kernel."""
     from oracle import hea_oracle as orc
     from quanonet_b200.ops import hea_expval_backward, plan_tier
     rng = np.random.default_rng(n)
@@ -402,7 +404,7 @@ for n in (6, 9, 10):
     assert max(errs) < 1e-5, (n, errs)
 print("LANES_OK")
 ''' % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__)))
-    env = dict(os.environ, QON_SMEM_FIRST_N="14")
+    env = dict(os.environ, QON_SMEM_FIRST_N="14", QON_WIDE_MAX_B="0")
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=600)
     assert "LANES_OK" in r.stdout, r.stdout + r.stderr
 
@@ -554,10 +556,10 @@ def test_throughput_tier_on_small_batches(cuda_device):
     subprocess with the latency tier disabled, so the one-thread-per-sample kernels (ragged tails, edge cases,
     wrapper cases) stay covered at those sizes too."""
     import subprocess, sys
-    env = dict(os.environ, QON_LANES_MAX_B="0")
+    env = dict(os.environ, QON_LANES_MAX_B="0", QON_WIDE_MAX_B="0")
     here = os.path.abspath(__file__)
     r = subprocess.run([sys.executable, "-m", "pytest", here, "-q", "-x", "-m", "gpu", "-k",
-                        "golden or edge or wrapper or published or closed_form or encoding"],
+                        "golden or edge or wrapper or published or closed_form or encoding or larger_qubit"],
                        env=env, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
 
