@@ -48,4 +48,26 @@ for B in (100, 5000, 20000):          # latency tier, latency tier, throughput t
     if rank == 0:
         print(f"world={world} B={B}/gpu: eager step fused-exchange {tf:.1f} us | separate peer all-reduce {tp:.1f} us | "
               f"NCCL {tn:.1f} us; grads bit-equal (fused vs peer), rel diff vs NCCL {worst:.1e}", flush=True)
+
+# HEAQNN with fixed frequencies (no frequency gradients, no bias): the flat layout is [ansatz | spare | sse | pad]
+from quanonet_b200.core.models_pt import HEAQNNPT
+def heaqnn(mode):
+    os.environ["QON_COLLECTIVE"] = "nccl" if mode == "nccl" else "peer"
+    torch.manual_seed(3)
+    m = HEAQNNPT(4, 9, (6, 2), scale_coeff=0.3, if_trainable_freq=False).to(dev)
+    tr = DataParallelTrainer(m, lr=1e-3)
+    if mode == "peer":
+        tr._fused_exchange = False
+    return tr
+fused, peer, nccl = heaqnn("fused"), heaqnn("peer"), heaqnn("nccl")
+assert fused._fused_exchange
+for it in range(10):
+    gen = torch.Generator().manual_seed(50 * it + rank)
+    u = torch.randn(300, 9, generator=gen).to(dev); y = torch.randn(300, 1, generator=gen).to(dev)
+    fused.step((u,), y); peer.step((u,), y); nccl.step((u,), y)
+    assert torch.equal(fused.flat_grad, peer.flat_grad)
+    assert torch.allclose(fused.flat_grad, nccl.flat_grad, rtol=1e-5, atol=1e-7)
+    assert torch.equal(fused.flat_param, peer.flat_param)
+if rank == 0:
+    print(f"world={world} HEAQNN fixed-frequency: fused exchange == separate peer all-reduce (bitwise), ~= NCCL", flush=True)
 dist.barrier(); dist.destroy_process_group()
