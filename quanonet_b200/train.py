@@ -126,7 +126,7 @@ class DataParallelTrainer:
             self.fused_encoding = standard and encoded_supported(q.n_wires, p0.dtype)
         # with the peer-memory exchange available, the fused step also does the all-reduce (one finalize kernel)
         from .comm import PeerAllReduce
-        self._fused_exchange = (self.fused_encoding and self.world_size > 1 and p0.dtype == torch.float32
+        self._fused_exchange = (self.fused_encoding and self.distributed and p0.dtype == torch.float32
                                 and isinstance(self._all_reduce, PeerAllReduce)
                                 and (self._freq_span is not None or not getattr(model, "if_trainable_freq", False))
                                 and q.ansatz_weights.requires_grad)

@@ -612,3 +612,39 @@ def test_peer_allreduce_single_rank(cuda_device):
                         os.path.join(root, "scripts", "peer_allreduce_check.py"), "50"],
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "iterations equal" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
+
+
+def test_fused_exchange_single_rank(cuda_device):
+    """qon_encoded_mse_step_dp (finalize + exchange in one kernel) on a one-rank NCCL group: gradients and
+    parameters must equal the separate-all-reduce path bit for bit over 20 steps at three batch sizes (latency
+    and throughput tiers), for QuanONet with trainable frequencies and HEAQNN with fixed ones.  World sizes 2 and
+    8: same script under torchrun on multi-GPU boxes (profiles/README.md)."""
+    import subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "1",
+                        "--master-addr", "127.0.0.1", "--master-port", "29578",
+                        os.path.join(root, "scripts", "dp_fused_exchange_check.py")],
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "HEAQNN fixed-frequency: fused exchange ==" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
+
+
+def test_latency_tier_falls_back_for_long_circuits(cuda_device):
+    """A circuit whose tables do not fit the latency tier's shared memory (1,500 sublayers) must run on the
+    one-thread-per-sample kernels instead, with the same results."""
+    from oracle import hea_oracle as O
+    from quanonet_b200.ops import hea_expval_backward
+    rng = np.random.default_rng(5)
+    n, K = 5, 750
+    depths = [2] * K
+    B = 3
+    x = rng.uniform(-np.pi, np.pi, (B, n * K)).astype(np.float32)
+    w = rng.uniform(-np.pi, np.pi, (2 * K, 3, n)).astype(np.float32)
+    g = rng.standard_normal(B).astype(np.float32)
+    ham = O.ham_from_bound(n)
+    off, co = O.ham_params(n)
+    e_ref, gx_ref, gw_ref = O.hea_forward_backward(x.astype(np.float64), w.astype(np.float64), n, [(n, 2)] * K, ham,
+                                                   g.astype(np.float64))
+    t = lambda a: torch.tensor(a, device=cuda_device)
+    e, gx, gw = hea_expval_backward(t(g), t(x), t(w), n, depths, None, 0, off, co, 0, True)
+    errs = (rel_l2(e.cpu().numpy()[:, 0], e_ref), rel_l2(gx.cpu().numpy(), gx_ref), rel_l2(gw.cpu().numpy(), gw_ref))
+    assert max(errs) < 5e-5, errs       # 7,500 rotations deep: rounding grows with sqrt(depth)
