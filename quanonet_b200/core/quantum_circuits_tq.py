@@ -24,7 +24,7 @@ import torch
 import torch.nn as nn
 
 from .. import _lib
-from ..ops import hea_expval
+from ..ops import hea_expval_autograd as hea_expval
 
 _PAULI_KIND = {"Z": _lib.QON_HAM_DIAG, "X": _lib.QON_HAM_PAULI_X, "Y": _lib.QON_HAM_PAULI_Y}
 _DIAG_ORDER = {"lsb0": _lib.QON_DIAG_LSB0, "msb0": _lib.QON_DIAG_MSB0}
