@@ -286,7 +286,7 @@ def test_fused_encoding_matches_unfused(cuda_device, tf, kind):
         torch.manual_seed(11)
         if kind == "quanonet":
             mk = lambda: QuanONetPT(n, 7, 2, (3, 2, 2, 1), scale_coeff=0.3, if_trainable_freq=tf, ham_bound=(-2.0, 4.0))
-            B = 5003      # above the small-batch (latency-layout) threshold so the fused-encoding kernels run
+            B = 5003      # latency tier here; the throughput tier runs it in test_throughput_tier_on_small_batches
             inputs = (torch.randn(B, 7), torch.rand(B, 2))
         else:
             mk = lambda: HEAQNNPT(n, 6, (4, 2, 0, 0), scale_coeff=0.4, if_trainable_freq=tf)
