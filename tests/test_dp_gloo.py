@@ -26,9 +26,14 @@ def _oracle_kernel(x, w, y, bias, grad_scale, qlayer, depths, need_gx):
     return t(e).reshape(-1, 1), t(g), (t(gx) if need_gx else torch.empty(0)), t(gw)
 
 
-def _make(seed=0):
-    from quanonet_b200.core.models_pt import QuanONetPT
+def _make(seed=0, kind="quanonet"):
+    from quanonet_b200.core.models_pt import HEAQNNPT, QuanONetPT
     torch.manual_seed(seed)
+    if kind == "heaqnn":        # no bias parameter: the flat gradient layout carries a spare slot instead
+        m = HEAQNNPT(2, 5, (3, 2), scale_coeff=0.3, if_trainable_freq=True).double()
+        with torch.no_grad():
+            m.freq.bias.uniform_(-1, 1)
+        return m
     m = QuanONetPT(2, 4, 1, (2, 1, 2, 2), scale_coeff=0.3, if_trainable_freq=True).double()
     with torch.no_grad():
         m.bias.fill_(0.1)
@@ -36,22 +41,29 @@ def _make(seed=0):
     return m
 
 
-def _data(B=12):
+def _data(B=12, kind="quanonet"):
     g = torch.Generator().manual_seed(5)
+    if kind == "heaqnn":
+        return (torch.randn(B, 5, generator=g, dtype=torch.float64), None,
+                torch.randn(B, 1, generator=g, dtype=torch.float64))
     return (torch.randn(B, 4, generator=g, dtype=torch.float64), torch.rand(B, 1, generator=g, dtype=torch.float64),
             torch.randn(B, 1, generator=g, dtype=torch.float64))
 
 
-def _worker(rank, world, port, out_dir):
+def _inputs(branch, trunk, sl=slice(None)):
+    return (branch[sl],) if trunk is None else (branch[sl], trunk[sl])
+
+
+def _worker(rank, world, port, out_dir, kind="quanonet"):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from quanonet_b200.train import DataParallelTrainer
-    model = _make(seed=rank)            # different init per rank: the trainer must broadcast rank 0's
+    model = _make(seed=rank, kind=kind)  # different init per rank: the trainer must broadcast rank 0's
     tr = DataParallelTrainer(model, lr=1e-2, optimizer="adam", kernel_fn=_oracle_kernel)
-    branch, trunk, y = _data()
+    branch, trunk, y = _data(kind=kind)
     sl = slice(rank * 6, (rank + 1) * 6)
-    loss = tr.step((branch[sl], trunk[sl]), y[sl])
+    loss = tr.step(_inputs(branch, trunk, sl), y[sl])
     torch.save({"loss": loss.item(), "grad": tr.flat_grad.clone(),
                 "params": {k: v.clone() for k, v in model.state_dict().items()}}, os.path.join(out_dir, f"r{rank}.pt"))
     dist.barrier()
@@ -66,9 +78,10 @@ def _free_port():
     return p
 
 
-def test_two_rank_gloo_matches_single_process(tmp_path):
+@pytest.mark.parametrize("kind", ["quanonet", "heaqnn"])
+def test_two_rank_gloo_matches_single_process(tmp_path, kind):
     from quanonet_b200.train import DataParallelTrainer
-    mp.spawn(_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, _free_port(), str(tmp_path), kind), nprocs=2, join=True)
     r0 = torch.load(tmp_path / "r0.pt")
     r1 = torch.load(tmp_path / "r1.pt")
     # replicas stay identical
@@ -77,10 +90,10 @@ def test_two_rank_gloo_matches_single_process(tmp_path):
     for k in r0["params"]:
         assert torch.equal(r0["params"][k], r1["params"][k]), k
     # and equal the single-process step on the whole batch
-    model = _make(seed=0)
+    model = _make(seed=0, kind=kind)
     tr = DataParallelTrainer(model, lr=1e-2, optimizer="adam", kernel_fn=_oracle_kernel)
-    branch, trunk, y = _data()
-    loss = tr.step((branch, trunk), y)
+    branch, trunk, y = _data(kind=kind)
+    loss = tr.step(_inputs(branch, trunk), y)
     assert loss.item() == pytest.approx(r0["loss"], rel=1e-10)
     assert torch.allclose(tr.flat_grad, r0["grad"], rtol=1e-9, atol=1e-12)
     for k, v in model.state_dict().items():
