@@ -154,7 +154,7 @@ int64_t qon_latency_tier_max_batch(void);
  * csrc/qon_peer.cuh).  `peer_bufs` is a HOST array of `world` device pointers to symmetric buffers of
  * qon_peer_buffer_bytes(max_len, world) bytes each, peer_bufs[rank] being this rank's own; the buffers must be
  * zero-filled once before first use and every rank must make the same sequence of calls.  src may equal dst.
- * A peer that does not show up within ~2 s poisons dst with NaN instead of hanging. */
+ * A peer that does not show up within ~30 s poisons dst with NaN instead of hanging. */
 size_t qon_peer_buffer_bytes(int64_t max_len, int world);
 int qon_peer_allreduce_f32(const float* src, float* dst, int64_t len, void* const* peer_bufs, int world, int rank,
                            int64_t max_len, void* stream);

@@ -653,7 +653,7 @@ int run(const Job& j) {
             const int rows = j.B > 0 ? pl.rows : 0;
             finalize_exchange_kernel<<<pl.S + K + 1, 256, 0, st>>>(
                 (const float*)p.mpart, rows, pl.rowlen, pl.vp, pl.fvp, n, pl.S, K, (const float*)j.w, j.flat, j.fl, j.peers,
-                j.world, j.rank, j.peer_max_len, 4000000000LL);
+                j.world, j.rank, j.peer_max_len, kPeerTimeoutCycles);
             cudaError_t e = cudaGetLastError();
             if (e != cudaSuccess) return fail((int)e, "finalize+exchange launch failed: %s", cudaGetErrorString(e));
         }
@@ -737,8 +737,7 @@ int qon_peer_allreduce_f32(const float* src, float* dst, int64_t len, void* cons
         if (!peer_bufs[p] || ((uintptr_t)peer_bufs[p] & 255)) return fail(QON_ERR_BAD_ARG, "peer buffer %d is NULL or not 256-byte aligned", p);
         pp.p[p] = (char*)peer_bufs[p];
     }
-    // ~2 s of SM clocks at the nominal 2 GHz (querying cudaDevAttrClockRate costs milliseconds per call)
-    const long long timeout = 4000000000LL;
+    const long long timeout = kPeerTimeoutCycles;   // (querying cudaDevAttrClockRate costs milliseconds per call)
     peer_allreduce_kernel<<<1, kPeerThreads, 0, (cudaStream_t)stream>>>(src, dst, (int)len, pp, world, rank, max_len, timeout);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail((int)e, "peer all-reduce launch failed: %s", cudaGetErrorString(e));

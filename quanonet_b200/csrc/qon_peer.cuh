@@ -8,8 +8,8 @@
 //               through NVSwitch; the local copy is an ordinary store);
 //   2. signal : __threadfence_system, CTA barrier, then lane p release-stores the epoch into peer p's flag
 //               word [rank];
-//   3. wait   : lane p acquire-spins on the local flag word [p] until it carries this epoch (bounded: on
-//               timeout the result is NaN-poisoned and an error word is set — never a hang);
+//   3. wait   : lane p acquire-spins on the local flag word [p] until it carries this epoch (bounded, ~30 s:
+//               on timeout the result is NaN-poisoned and an error word is set — never a hang);
 //   4. reduce : out[i] = sum_p slot[set][p][i] in rank order — every rank adds the same numbers in the same
 //               order, so replicas stay bit-identical.
 // Slots are double-buffered by epoch parity: a rank can start epoch e+2 (same set as e) only after every peer
@@ -25,6 +25,9 @@ namespace qon {
 constexpr int kPeerMaxWorld = 8;
 constexpr int kPeerHeaderBytes = 256;    // [0,128): flag words [world]; 128: epoch counter; 132: error word
 constexpr int kPeerThreads = 1024;
+// how long a rank waits for its peers before giving up (~30 s of SM clocks): long enough for a rank that is busy
+// on the host (checkpoint I/O, evaluation) between steps, short enough that a dead peer never hangs the GPU
+constexpr long long kPeerTimeoutCycles = 60000000000LL;
 
 struct PeerPtrs { char* p[kPeerMaxWorld]; };
 

@@ -162,6 +162,10 @@ class B200Solver:
                 loss_sum += loss
                 sse += loss * gb
             avg = float(loss_sum) / num_batches                   # one host sync per epoch
+            ar = getattr(self.trainer, "_all_reduce", None)
+            if hasattr(ar, "timed_out") and ar.timed_out():
+                raise RuntimeError("the peer-memory all-reduce gave up waiting for a rank (~30 s); gradients of that "
+                                   "step were NaN-poisoned — check that every rank is alive, or set QON_COLLECTIVE=nccl")
             rel = float(torch.sqrt(sse) / (torch.linalg.norm(self.train_out) + 1e-8))
             history["loss_train"].append(avg)
             history["rel_l2_train"].append(rel)
