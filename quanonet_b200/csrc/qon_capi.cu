@@ -484,6 +484,7 @@ int make_plan(int64_t B, int n, int K, const int* depth, int dtype, int mode, Pl
             pl->lq = n;
             warps = pl->wp.threads / 32;
             blocks_per_sm = pl->wp.blocks_per_sm;
+            // (capping the resident CTAs to shrink the partial-row table was measured: slower at every batch size)
         } else {
             RegLaunchInfo ri = reg_info_cached(dev, dtype, pl->nl, pl->lq, mode);
             if (!ri.ok)
