@@ -22,27 +22,28 @@ WarpKern<T> warp_kernel_n(int mode) {
     }
 }
 
-template <int N>
-WarpKern<float> warp_wide_kernel_n(int mode) {
+template <typename T, int N>
+WarpKern<T> warp_wide_kernel_n(int mode) {
     switch (mode) {
-        case 0: return hea_warp_wide_kernel<N, false, false, kWarpThreads>;
-        case 1: return hea_warp_wide_kernel<N, true, true, kWarpThreads>;
-        case 2: return hea_warp_wide_kernel<N, true, false, kWarpThreads>;
+        case 0: return hea_warp_wide_kernel<T, N, false, false, kWarpThreads>;
+        case 1: return hea_warp_wide_kernel<T, N, true, true, kWarpThreads>;
+        case 2: return hea_warp_wide_kernel<T, N, true, false, kWarpThreads>;
         default: return nullptr;
     }
 }
 
 template <typename T>
 WarpKern<T> warp_kernel(int n, int mode) {
-    if constexpr (sizeof(T) == 4) {     // n = 6..10: several amplitudes per lane (hea_warp_wide.cuh), fp32, x given
-        switch (n) {
-            case 6: return warp_wide_kernel_n<6>(mode);
-            case 7: return warp_wide_kernel_n<7>(mode);
-            case 8: return warp_wide_kernel_n<8>(mode);
-            case 9: return warp_wide_kernel_n<9>(mode);
-            case 10: return warp_wide_kernel_n<10>(mode);
-            default: break;
-        }
+    // n = 6..10 (fp64: 6..9): several amplitudes per lane (hea_warp_wide.cuh), x given
+    switch (n) {
+        case 6: return warp_wide_kernel_n<T, 6>(mode);
+        case 7: return warp_wide_kernel_n<T, 7>(mode);
+        case 8: return warp_wide_kernel_n<T, 8>(mode);
+        case 9: return warp_wide_kernel_n<T, 9>(mode);
+        case 10:
+            if constexpr (sizeof(T) == 4) return warp_wide_kernel_n<T, 10>(mode);
+            else return nullptr;
+        default: break;
     }
     switch (n) {
         case 1: return warp_kernel_n<T, 1>(mode);

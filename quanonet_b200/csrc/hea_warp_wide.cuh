@@ -1,4 +1,5 @@
-// Small-batch latency tier for n = 6..10 (fp32, angles given): ONE WARP PER SAMPLE, 2^(n-5) amplitudes per lane.
+// Small-batch latency tier for n = 6..10 (fp32; fp64 up to n = 9; angles given): ONE WARP PER SAMPLE, 2^(n-5)
+// amplitudes per lane.
 //
 // Same idea as hea_warp.cuh, one step wider: the low NL = n-5 qubits index the registers of a lane, the top 5
 // index the lanes.  In-lane gates are plain FMAs on register pairs, lane gates exchange every register with
@@ -13,9 +14,8 @@
 
 namespace qon {
 
-template <int N, bool GRAD, bool NEED_GX, int THREADS>
-__global__ void __launch_bounds__(THREADS) hea_warp_wide_kernel(const HeaParams<float> p, const DepthPack dp) {
-    using T = float;
+template <typename T, int N, bool GRAD, bool NEED_GX, int THREADS>
+__global__ void __launch_bounds__(THREADS) hea_warp_wide_kernel(const HeaParams<T> p, const DepthPack dp) {
     constexpr int LQ = 5, NL = N - LQ, NA = 1 << NL;
     constexpr int VP = moment_slots(N);          // 32 for n = 6..10: after the butterfly lane l holds slot l
     constexpr int FVP = freq_slots(N);

@@ -357,14 +357,18 @@ int64_t lanes_max_batch() {
 
 // Largest batch the wide latency tier (n = 6..10, hea_warp_wide.cuh) serves; above it the shared-memory tier's
 // throughput wins.  QON_WIDE_MAX_B overrides every entry (0 disables).
-int64_t wide_max_batch(int n) {
+int64_t wide_max_batch(int n, int dtype) {
     static const int64_t ov = [] { const char* e = getenv("QON_WIDE_MAX_B"); return e ? (int64_t)atoll(e) : (int64_t)-1; }();
     if (ov >= 0) return ov;
     // measured against the shared-memory tier (fwd+grad, 60 sublayers; scripts/small_batch_widths.py): n = 6: 103 us vs
     // 785 us at B = 100, level at ~8,000; n = 8: 171 vs 934 us, level at ~4,000; n = 9: 480 vs 1,033 us, level at
     // ~1,500; n = 10 (32 amplitudes per lane, 255 registers): 1,215 vs 1,110 us — not used
     static const int64_t tbl[5] = {8192, 4096, 2048, 1024, 0};      // n = 6..10
-    return n >= 6 && n <= 10 ? tbl[n - 6] : 0;
+    // fp64 (vs the lane-distributed register kernels; B = 100 / 2,000): n = 6: 110 / 270 us vs 642 / 654; n = 7:
+    // 155 / 447 vs 815 / 839; n = 8: 277 / 876 vs 966 / 1,041; n = 9: 533 / 2,216 vs 1,182 / 2,473
+    static const int64_t tbl64[5] = {2048, 2048, 2048, 1024, 0};     // fp64, n = 6..9
+    if (n < 6 || n > 10) return 0;
+    return dtype == QON_F32 ? tbl[n - 6] : tbl64[n - 6];
 }
 
 // QON_HBM_TIER=generic falls back to the one-CTA-per-sample kernel for n >= 14 (experiments / A-B tests)
@@ -426,7 +430,7 @@ int make_plan(int64_t B, int n, int K, const int* depth, int dtype, int mode, Pl
     pl->fast_smem = false;
     pl->fast_hbm = false;
     pl->fast_warp = false;
-    if (dtype == QON_F32 && !mode_is_enc(mode) && n >= 6 && n <= 10 && B <= wide_max_batch(n)) {
+    if (!mode_is_enc(mode) && n >= 6 && n <= (dtype == QON_F32 ? 10 : 9) && B <= wide_max_batch(n, dtype)) {
         pl->wp = warp_plan(n, K, (int)S, (int)es, mode);
         pl->fast_warp = pl->wp.ok;
     }
