@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define QON_ABI_VERSION 1
+#define QON_ABI_VERSION 2   /* 2: + qon_latency_tier_max_batch, qon_peer_*, qon_encoded_mse_step_dp */
 
 /* dtype: arithmetic type of x, w, out, gradients and the state */
 #define QON_F32 0 /* float32 / complex64  — parity with the TorchQuantum path            */

@@ -16,7 +16,7 @@ LIB_PATH = os.environ.get("QON_LIB_PATH") or os.path.join(PKG_DIR, "libquanonet_
 QON_F32, QON_F64 = 0, 1
 QON_HAM_DIAG, QON_HAM_PAULI_X, QON_HAM_PAULI_Y = 0, 1, 2
 QON_DIAG_LSB0, QON_DIAG_MSB0 = 0, 1
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 # every symbol include/quanonet_b200.h declares
 EXPORTED_SYMBOLS = (
