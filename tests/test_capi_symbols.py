@@ -51,3 +51,15 @@ def test_argument_errors_are_reported_without_a_gpu(lib):
     assert lib.qon_workspace_bytes(10, 5, 2, depth, 7, 1) == 0
     rc = lib.qon_hea_forward(None, 10, None, None, 4, 5, 2, depth, None, 0, 0.0, 1.0, 0, 3, None, 0, None)
     assert rc < 0
+
+
+def test_host_only_entry_points(lib):
+    """Planning helpers and the host-side checks of the exchange entry points need no device."""
+    assert lib.qon_latency_tier_max_batch() >= 0
+    assert lib.qon_peer_buffer_bytes(2402, 8) == 256 + 2 * 8 * 2402 * 4
+    assert lib.qon_peer_buffer_bytes(2402, 9) == 0            # one node: at most 8 ranks
+    bufs = (ctypes.c_void_p * 2)(None, None)
+    assert lib.qon_peer_allreduce_f32(None, None, 10, bufs, 2, 0, 10, None) < 0
+    assert b"non-NULL" in lib.qon_last_error()
+    assert lib.qon_peer_allreduce_f32(ctypes.c_void_p(256), ctypes.c_void_p(256), 10, bufs, 2, 5, 10, None) < 0
+    assert b"rank" in lib.qon_last_error()
