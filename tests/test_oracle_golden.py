@@ -149,3 +149,44 @@ def test_diag_index_orders_differ_unless_symmetric():
     for order in ("lsb0", "msb0"):
         b = orc.hea_forward(x, w, 3, blocks, orc.ham_from_diag(0.5 + 1.5 * zs, 3, order))
         assert np.abs(a - b).max() < 1e-13
+
+
+def test_oracle_properties_on_random_circuits():
+    """Randomised (hypothesis) properties of the oracle itself: the expectation value lies in the spectrum of H,
+    the adjoint gradient is linear in the upstream gradient and matches a central finite difference on a
+    randomly chosen shared angle and a randomly chosen encoding angle."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=25, deadline=None)
+    @given(n=st.integers(1, 4), depths=st.lists(st.integers(1, 3), min_size=1, max_size=3),
+           kind=st.sampled_from(["X", "Y", "Z", "diag"]), seed=st.integers(0, 10_000))
+    def check(n, depths, kind, seed):
+        rng = np.random.default_rng(seed)
+        blocks = [(n, d) for d in depths]
+        K, S, B = len(depths), sum(depths), 3
+        x = rng.uniform(-np.pi, np.pi, (B, n * K))
+        w = rng.uniform(-np.pi, np.pi, (S, 3, n))
+        if kind == "diag":
+            d = rng.uniform(-3, 3, 1 << n)
+            ham, lo, hi = orc.ham_from_diag(d, n), d.min(), d.max()
+        else:
+            off, co = 0.4, 0.9
+            ham, lo, hi = orc.Ham("pauli", kind, off, co), off - n * abs(co), off + n * abs(co)
+        g = rng.standard_normal(B)
+        e, gx, gw = orc.hea_forward_backward(x, w, n, blocks, ham, g)
+        assert np.all(e >= lo - 1e-9) and np.all(e <= hi + 1e-9)
+        _, gx2, gw2 = orc.hea_forward_backward(x, w, n, blocks, ham, 2.5 * g)
+        assert np.allclose(gx2, 2.5 * gx, atol=1e-12) and np.allclose(gw2, 2.5 * gw, atol=1e-12)
+        h = 1e-6
+        s_, g_, q_ = rng.integers(S), rng.integers(3), rng.integers(n)
+        wp, wm = w.copy(), w.copy()
+        wp[s_, g_, q_] += h; wm[s_, g_, q_] -= h
+        fd = (g * (orc.hea_forward(x, wp, n, blocks, ham) - orc.hea_forward(x, wm, n, blocks, ham))).sum() / (2 * h)
+        assert abs(fd - gw[s_, g_, q_]) < 1e-6 * max(1.0, abs(fd))
+        b_, c_ = rng.integers(B), rng.integers(n * K)
+        xp, xm = x.copy(), x.copy()
+        xp[b_, c_] += h; xm[b_, c_] -= h
+        fdx = g[b_] * (orc.hea_forward(xp, w, n, blocks, ham)[b_] - orc.hea_forward(xm, w, n, blocks, ham)[b_]) / (2 * h)
+        assert abs(fdx - gx[b_, c_]) < 1e-6 * max(1.0, abs(fdx))
+
+    check()
