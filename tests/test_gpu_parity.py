@@ -648,3 +648,41 @@ def test_latency_tier_falls_back_for_long_circuits(cuda_device):
     e, gx, gw = hea_expval_backward(t(g), t(x), t(w), n, depths, None, 0, off, co, 0, True)
     errs = (rel_l2(e.cpu().numpy()[:, 0], e_ref), rel_l2(gx.cpu().numpy(), gx_ref), rel_l2(gw.cpu().numpy(), gw_ref))
     assert max(errs) < 5e-5, errs       # 7,500 rotations deep: rounding grows with sqrt(depth)
+
+
+def test_random_configs_vs_oracle(cuda_device):
+    """60 seeded random problems (n = 1..9, 1..4 blocks of depth 1..3, every observable kind, ragged batches from 1 to
+    700 samples, fp32 and fp64, with and without dL/dx) against the fp64 oracle — whatever tier the planner picks."""
+    from oracle import hea_oracle as O
+    from quanonet_b200.ops import hea_expval, hea_expval_backward, plan_tier
+    rng = np.random.default_rng(2024)
+    for case in range(60):
+        n = int(rng.integers(1, 10))
+        depths = [int(d) for d in rng.integers(1, 4, size=int(rng.integers(1, 5)))]
+        K, S = len(depths), sum(depths)
+        B = int(rng.choice([1, 2, 5, 31, 33, 100, 257, 700]))
+        kind = int(rng.integers(0, 4))          # 0: Z sum, 1: X sum, 2: Y sum, 3: diagonal
+        dtype, tol = ((torch.float32, TOL_F32) if rng.random() < 0.6 else (torch.float64, 1e-11))
+        need_gx = bool(rng.random() < 0.7)
+        x = rng.uniform(-np.pi, np.pi, (B, n * K)).astype(np.float32)
+        w = rng.uniform(-np.pi, np.pi, (S, 3, n)).astype(np.float32)
+        g = rng.standard_normal(B).astype(np.float32)
+        off, co = float(rng.uniform(-1, 1)), float(rng.uniform(0.2, 1.5))
+        if kind == 3:
+            diag = rng.uniform(-2, 2, 1 << n)
+            ham, hd, args = O.ham_from_diag(diag, n), diag, (0, 0.0, 1.0, 0)
+        else:
+            ham, hd = O.Ham("pauli", "ZXY"[kind], off, co), None
+            args = (0, off, co, kind)
+        e_ref, gx_ref, gw_ref = O.hea_forward_backward(x.astype(np.float64), w.astype(np.float64), n,
+                                                       [(n, d) for d in depths], ham, g.astype(np.float64))
+        t = lambda a: torch.tensor(a, dtype=dtype, device=cuda_device)
+        hdt = None if hd is None else t(hd)
+        e, gx, gw = hea_expval_backward(t(g), t(x), t(w), n, depths, hdt, *args, need_gx)
+        f = hea_expval(t(x), t(w), n, depths, hdt, *args)
+        scale = max(np.linalg.norm(e_ref), 1e-3 * np.sqrt(B))      # E can be ~0 for X/Y sums
+        errs = [np.linalg.norm(e.cpu().numpy()[:, 0] - e_ref) / scale, np.linalg.norm(f.cpu().numpy()[:, 0] - e_ref) / scale,
+                rel_l2(gw.cpu().numpy(), gw_ref)]
+        if need_gx:
+            errs.append(rel_l2(gx.cpu().numpy(), gx_ref))
+        assert max(errs) < tol, (case, n, depths, B, kind, dtype, need_gx, plan_tier(B, n, dtype), errs)
