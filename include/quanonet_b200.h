@@ -114,7 +114,8 @@ int qon_hea_mse_forward_backward(const void* x, int64_t ldx, const void* w, cons
  * _TiledElementWise / _ScaleRepeat (core/models_pt.py:14-68):  x[b,c] = fw[c] * u_src(c)[b, local(c) % in] + fb[c],
  * src(c) = source 0 (trunk) for the first K0 blocks, source 1 (branch) afterwards; local(c) = column index
  * within its source.  These entry points evaluate that inside the kernel, so x and grad_x (1.2 KB per sample
- * each at Q5 Net40-2-20-2) are never materialised.  Register tier only (n <= 5 fp32, n <= 4 fp64).
+ * each at Q5 Net40-2-20-2) are never materialised.  Built for n <= 5 (fp32) / n <= 4 (fp64) at any batch size and
+ * for n = 6..9 (fp32) at latency-tier batch sizes — qon_encoded_supported() tells.
  *   u0  device (B, in0) row stride ldu0 — may be NULL when K0 == 0 (HEAQNN);   u1  device (B, in1), stride ldu1
  *   fw  device (n*K,) frequency weights (fixed-scale mode: the constant scale);  fb  device (n*K,) or NULL
  */
@@ -146,6 +147,11 @@ int qon_plan_tier(int64_t B, int n, int dtype, int need_grad, int* lanes_log2);
  * lane, see csrc/hea_warp.cuh); larger batches use the one-thread-per-sample throughput layout.  Callers that
  * can choose between the x-given and the fused-encoding entry points use it to pick the faster one. */
 int64_t qon_latency_tier_max_batch(void);
+
+/* 1 if the fused-encoding entry points (qon_encoded_forward / qon_encoded_mse_step[_dp]) have a kernel for a batch of
+ * B samples at n qubits in `dtype` on the current device, else 0: n <= 5 (fp32) / n <= 4 (fp64) at any batch size,
+ * and n = 6..9 in fp32 for batches small enough for the wide latency tier. */
+int qon_encoded_supported(int64_t B, int n, int dtype, int need_grad);
 
 /* Exchange step of the data-parallel training step (the reference has no multi-GPU path — main.py:52
  * pins one GPU — so this replaces the torch.distributed all_reduce a DDP port would add at

@@ -30,6 +30,7 @@ EXPORTED_SYMBOLS = (
     "qon_encoded_mse_step",
     "qon_plan_tier",
     "qon_latency_tier_max_batch",
+    "qon_encoded_supported",
     "qon_peer_buffer_bytes",
     "qon_peer_allreduce_f32",
     "qon_encoded_mse_step_dp",
@@ -68,6 +69,8 @@ def _declare(lib):
     lib.qon_encoded_forward.argtypes = enc_head + [vp, vp, i64, i32, i32, ip] + ham_tail
     lib.qon_encoded_mse_step.restype = i32
     lib.qon_encoded_mse_step.argtypes = enc_head + [vp, vp, vp, dbl, vp, vp, vp, vp, vp, i64, i32, i32, ip] + ham_tail
+    lib.qon_encoded_supported.restype = i32
+    lib.qon_encoded_supported.argtypes = [i64, i32, i32, i32]
     lib.qon_latency_tier_max_batch.restype = i64
     lib.qon_latency_tier_max_batch.argtypes = []
     lib.qon_peer_buffer_bytes.restype = sz

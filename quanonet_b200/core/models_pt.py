@@ -73,7 +73,7 @@ def _can_fuse_inference(qlayer, u):
         return False
     from ..ops import encoded_supported
     w = qlayer.ansatz_weights
-    return (encoded_supported(qlayer.n_wires, w.dtype)
+    return (encoded_supported(qlayer.n_wires, w.dtype, int(u.shape[0]), need_grad=False)
             and all(e == qlayer.n_wires and d >= 1 for e, d in qlayer.block_configs))
 
 

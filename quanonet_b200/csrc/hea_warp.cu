@@ -25,11 +25,20 @@ WarpKern<T> warp_kernel_n(int mode) {
 template <typename T, int N>
 WarpKern<T> warp_wide_kernel_n(int mode) {
     switch (mode) {
-        case 0: return hea_warp_wide_kernel<T, N, false, false, kWarpThreads>;
-        case 1: return hea_warp_wide_kernel<T, N, true, true, kWarpThreads>;
-        case 2: return hea_warp_wide_kernel<T, N, true, false, kWarpThreads>;
-        default: return nullptr;
+        case 0: return hea_warp_wide_kernel<T, N, false, false, 0, kWarpThreads>;
+        case 1: return hea_warp_wide_kernel<T, N, true, true, 0, kWarpThreads>;
+        case 2: return hea_warp_wide_kernel<T, N, true, false, 0, kWarpThreads>;
+        default: break;
     }
+    if constexpr (sizeof(T) == 4 && N <= 9) {      // fused-encoding modes: fp32, n = 6..9
+        switch (mode) {
+            case 3: return hea_warp_wide_kernel<T, N, false, false, 1, kWarpThreads>;
+            case 4: return hea_warp_wide_kernel<T, N, true, false, 1, kWarpThreads>;
+            case 5: return hea_warp_wide_kernel<T, N, true, false, 2, kWarpThreads>;
+            default: break;
+        }
+    }
+    return nullptr;
 }
 
 template <typename T>

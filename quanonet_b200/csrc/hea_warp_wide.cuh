@@ -14,8 +14,12 @@
 
 namespace qon {
 
-template <typename T, int N, bool GRAD, bool NEED_GX, int THREADS>
+//   ENC as in hea_warp.cuh: 0 angles given, 1 frequency layers evaluated in-kernel, 2 also their gradients.
+template <typename T, int N, bool GRAD, bool NEED_GX, int ENC, int THREADS>
 __global__ void __launch_bounds__(THREADS) hea_warp_wide_kernel(const HeaParams<T> p, const DepthPack dp) {
+    constexpr bool FREQ_GRAD = GRAD && ENC == 2;
+    constexpr bool WANT_GX = NEED_GX || FREQ_GRAD;
+    static_assert(!(NEED_GX && ENC != 0), "grad_x is only materialised when x is");
     constexpr int LQ = 5, NL = N - LQ, NA = 1 << NL;
     constexpr int VP = moment_slots(N);          // 32 for n = 6..10: after the butterfly lane l holds slot l
     constexpr int FVP = freq_slots(N);
@@ -27,10 +31,11 @@ __global__ void __launch_bounds__(THREADS) hea_warp_wide_kernel(const HeaParams<
     const int S = p.S, K = p.K, SN = p.S * N, KN = p.K * N;
     Vec4<T>* uc_s = reinterpret_cast<Vec4<T>*>(warp_smem);
     Vec4<T>* rc_s = uc_s + SN;
-    Vec2<T>* sc_all = reinterpret_cast<Vec2<T>*>(uc_s + (NEED_GX ? 2 : 1) * SN);
+    Vec2<T>* sc_all = reinterpret_cast<Vec2<T>*>(uc_s + (WANT_GX ? 2 : 1) * SN);
+    T* uv_all = reinterpret_cast<T*>(sc_all + (size_t)WARPS * KN);          // FREQ_GRAD only
     for (int i = threadIdx.x; i < SN; i += THREADS) {
         uc_s[i] = ldg4(p.ucoef + i);
-        if constexpr (NEED_GX) rc_s[i] = ldg4(p.rcoef + i);
+        if constexpr (WANT_GX) rc_s[i] = ldg4(p.rcoef + i);
     }
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -41,11 +46,13 @@ __global__ void __launch_bounds__(THREADS) hea_warp_wide_kernel(const HeaParams<
 #pragma unroll
     for (int j = 0; j <= LQ - 2; ++j) pr ^= ((pr >> (j + 1)) & 1) << j;     // reverse: gather source
     Vec2<T>* sc = sc_all + (size_t)warp * KN;
+    T* uv = FREQ_GRAD ? uv_all + (size_t)warp * KN : nullptr;    // source value u of every encoding column
 
     const int64_t gwarp = (int64_t)blockIdx.x * WARPS + warp;
     const int64_t nwarps = (int64_t)gridDim.x * WARPS;
     T* mrow = GRAD ? p.mpart + gwarp * p.rowlen : nullptr;
-    T* srow = GRAD ? mrow + (int64_t)S * VP + (int64_t)K * FVP : nullptr;
+    T* frow = GRAD ? mrow + (int64_t)S * VP : nullptr;
+    T* srow = GRAD ? frow + (int64_t)K * FVP : nullptr;
     __syncthreads();
 
     // ring = CNOT(control (i+1)%N -> target i), i = 0..N-1, applied in that order (REVERSE: undone in reverse)
@@ -81,13 +88,25 @@ __global__ void __launch_bounds__(THREADS) hea_warp_wide_kernel(const HeaParams<
         const bool valid = b < p.B;
         const int64_t bc = valid ? b : p.B - 1;
         __syncwarp();
-        {
+        if constexpr (ENC == 0) {
             const T* xrow = p.x + bc * p.ldx;
 #pragma unroll 4
             for (int c = lane; c < KN; c += 32) {
                 T sn, cs;
                 sincos_half(__ldg(xrow + c), sn, cs);
                 sc[c] = Vec2<T>{sn, cs};
+            }
+        } else {
+            const T* u0row = p.u0 ? p.u0 + bc * p.ldu0 : nullptr;
+            const T* u1row = p.u1 + bc * p.ldu1;
+            const int c0 = p.K0 * N;                       // columns below c0 read source 0
+#pragma unroll 4
+            for (int c = lane; c < KN; c += 32) {
+                const T u = __ldg((c < c0 ? u0row : u1row) + __ldg(p.uidx + c));
+                T sn, cs;
+                sincos_half(fma_(u, __ldg(p.fw + c), p.fb ? __ldg(p.fb + c) : T(0)), sn, cs);
+                sc[c] = Vec2<T>{sn, cs};
+                if constexpr (FREQ_GRAD) uv[c] = u;
             }
         }
         __syncwarp();
@@ -152,13 +171,20 @@ __global__ void __launch_bounds__(THREADS) hea_warp_wide_kernel(const HeaParams<
                     });
                     const T tot = butterfly_reduce<T, VP>(mv, lane);      // lane l holds slot l
                     atomicAdd(mrow + (int64_t)s * VP + lane, tot);
-                    if constexpr (NEED_GX) {
+                    if constexpr (WANT_GX) {
                         if (j == 0) {   // the warp is the sample: the totals are its own moments
                             const int q3 = (lane < N ? lane : 0) * 3;
                             const T mx = shfl_idx_(tot, q3), my = shfl_idx_(tot, q3 + 1), mz = shfl_idx_(tot, q3 + 2);
-                            if (lane < N && valid) {
+                            if (lane < N) {
                                 const Vec4<T> r = rc_s[s * N + lane];
-                                gxrow[(int64_t)k * N + lane] = fma_(r.z, mz, fma_(r.y, my, r.x * mx));
+                                const T gxv = fma_(r.z, mz, fma_(r.y, my, r.x * mx));
+                                if constexpr (NEED_GX) {
+                                    if (valid) gxrow[(int64_t)k * N + lane] = gxv;
+                                }
+                                if constexpr (FREQ_GRAD) {   // theta = fw*u + fb  =>  d/dfw = gx*u, d/dfb = gx (g = 0 if invalid)
+                                    atomicAdd(frow + k * FVP + 2 * lane, gxv * uv[k * N + lane]);
+                                    atomicAdd(frow + k * FVP + 2 * lane + 1, gxv);
+                                }
                             }
                         }
                     }

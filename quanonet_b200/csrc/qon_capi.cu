@@ -430,7 +430,8 @@ int make_plan(int64_t B, int n, int K, const int* depth, int dtype, int mode, Pl
     pl->fast_smem = false;
     pl->fast_hbm = false;
     pl->fast_warp = false;
-    if (!mode_is_enc(mode) && n >= 6 && n <= (dtype == QON_F32 ? 10 : 9) && B <= wide_max_batch(n, dtype)) {
+    if ((!mode_is_enc(mode) || (dtype == QON_F32 && n <= 9)) && n >= 6 && n <= (dtype == QON_F32 ? 10 : 9) &&
+        B <= wide_max_batch(n, dtype)) {
         pl->wp = warp_plan(n, K, (int)S, (int)es, mode);
         pl->fast_warp = pl->wp.ok;
     }
@@ -725,6 +726,13 @@ size_t qon_workspace_bytes(int64_t B, int n, int K, const int* depth_per_block, 
 }
 
 int64_t qon_latency_tier_max_batch(void) { return lanes_max_batch(); }
+
+int qon_encoded_supported(int64_t B, int n, int dtype, int need_grad) {
+    Plan pl;
+    int one = 1;
+    const int rc = make_plan(B, n, 1, &one, dtype, need_grad ? 5 : 3, &pl);
+    return rc == 0 ? 1 : 0;
+}
 
 size_t qon_peer_buffer_bytes(int64_t max_len, int world) {
     if (max_len < 1 || world < 1 || world > kPeerMaxWorld) return 0;

@@ -409,6 +409,12 @@ def _(u0, u1, fw, fb, K0, weights, target, bias, grad_scale, n_wires, depth_per_
     return torch.empty_like(weights), g, u1.new_empty(g.shape), u1.new_empty((2,))
 
 
-def encoded_supported(n_wires: int, dtype=torch.float32) -> bool:
-    """Fused-encoding kernels exist for one-thread-per-sample layouts: n <= 5 (fp32) / n <= 4 (fp64)."""
-    return n_wires <= (5 if dtype == torch.float32 else 4)
+def encoded_supported(n_wires: int, dtype=torch.float32, batch: Optional[int] = None, need_grad: bool = True) -> bool:
+    """Whether the fused-encoding kernels serve this problem: always for n <= 5 (fp32) / n <= 4 (fp64); for
+    n = 6..9 in fp32 only when ``batch`` is given and small enough for the wide latency tier
+    (``qon_encoded_supported`` asks the planner)."""
+    if n_wires <= (5 if dtype == torch.float32 else 4):
+        return True
+    if batch is None or dtype != torch.float32 or not 6 <= n_wires <= 9:
+        return False
+    return bool(_lib.load().qon_encoded_supported(int(batch), int(n_wires), _DTYPES[dtype], int(need_grad)))

@@ -118,15 +118,20 @@ class DataParallelTrainer:
         # needs the register tier with one thread per sample and the standard n-angles-per-block layout
         self.kernel_events = None      # set to a list to collect (start, end) CUDA events around the kernel call
         self.fused_encoding = False
+        self._enc_by_batch = None
         self._const_freq = None
         if kernel_fn is None and use_fused_encoding and p0.is_cuda:
             from .ops import encoded_supported
             q = model.quantum_layer
             standard = all(e == q.n_wires and d >= 1 for e, d in q.block_configs)
             self.fused_encoding = standard and encoded_supported(q.n_wires, p0.dtype)
+            # n = 6..9 (fp32): fused-encoding kernels exist for small batches only (wide latency tier) — decided per step
+            self._enc_by_batch = {} if standard and not self.fused_encoding and p0.dtype == torch.float32 \
+                and 6 <= q.n_wires <= 9 else None
         # with the peer-memory exchange available, the fused step also does the all-reduce (one finalize kernel)
         from .comm import PeerAllReduce
-        self._fused_exchange = (self.fused_encoding and self.distributed and p0.dtype == torch.float32
+        self._fused_exchange = ((self.fused_encoding or self._enc_by_batch is not None) and self.distributed
+                                and p0.dtype == torch.float32
                                 and isinstance(self._all_reduce, PeerAllReduce)
                                 and (self._freq_span is not None or not getattr(model, "if_trainable_freq", False))
                                 and q.ansatz_weights.requires_grad)
@@ -141,7 +146,13 @@ class DataParallelTrainer:
         B = y.shape[0]
         gB = global_batch if global_batch is not None else B * self.world_size
         scale = 2.0 / gB
-        if self.fused_encoding:
+        fused = self.fused_encoding
+        if not fused and self._enc_by_batch is not None:
+            fused = self._enc_by_batch.get(B)
+            if fused is None:
+                from .ops import encoded_supported
+                fused = self._enc_by_batch[B] = encoded_supported(q.n_wires, q.ansatz_weights.dtype, B)
+        if fused:
             return self._compute_grads_fused(inputs, y, scale, gB)
         if self.is_onet:
             branch, trunk = inputs

@@ -70,4 +70,28 @@ for it in range(10):
     assert torch.equal(fused.flat_param, peer.flat_param)
 if rank == 0:
     print(f"world={world} HEAQNN fixed-frequency: fused exchange == separate peer all-reduce (bitwise), ~= NCCL", flush=True)
+
+# n = 7: fused encoding + fused exchange on the wide latency tier (decided per batch size)
+from quanonet_b200.core.models_pt import QuanONetPT
+def q7(mode):
+    os.environ["QON_COLLECTIVE"] = "nccl" if mode == "nccl" else "peer"
+    torch.manual_seed(5)
+    m = QuanONetPT(7, 9, 2, (3, 2, 2, 1), scale_coeff=0.3, if_trainable_freq=True).to(dev)
+    tr = DataParallelTrainer(m, lr=1e-3)
+    if mode == "peer":
+        tr._fused_exchange = False
+    return tr
+fused, peer, nccl = q7("fused"), q7("peer"), q7("nccl")
+assert fused._fused_exchange and fused._enc_by_batch is not None
+for it in range(10):
+    gen = torch.Generator().manual_seed(70 * it + rank)
+    b = torch.randn(200, 9, generator=gen).to(dev); t = torch.rand(200, 2, generator=gen).to(dev)
+    y = torch.randn(200, 1, generator=gen).to(dev)
+    fused.step((b, t), y); peer.step((b, t), y); nccl.step((b, t), y)
+    assert torch.equal(fused.flat_grad, peer.flat_grad)
+    assert torch.allclose(fused.flat_grad, nccl.flat_grad, rtol=1e-5, atol=1e-7)
+    assert torch.equal(fused.flat_param, peer.flat_param)
+assert fused._enc_by_batch == {200: True}
+if rank == 0:
+    print(f"world={world} QuanONet Q7 (wide latency tier): fused exchange == separate peer all-reduce (bitwise), ~= NCCL", flush=True)
 dist.barrier(); dist.destroy_process_group()

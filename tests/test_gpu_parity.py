@@ -625,7 +625,8 @@ def test_fused_exchange_single_rank(cuda_device):
                         "--master-addr", "127.0.0.1", "--master-port", "29578",
                         os.path.join(root, "scripts", "dp_fused_exchange_check.py")],
                        capture_output=True, text=True, timeout=900)
-    assert r.returncode == 0 and "HEAQNN fixed-frequency: fused exchange ==" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
+    assert r.returncode == 0 and "HEAQNN fixed-frequency: fused exchange ==" in r.stdout \
+        and "Q7 (wide latency tier): fused exchange ==" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
 
 
 def test_latency_tier_falls_back_for_long_circuits(cuda_device):
@@ -686,3 +687,47 @@ def test_random_configs_vs_oracle(cuda_device):
         if need_gx:
             errs.append(rel_l2(gx.cpu().numpy(), gx_ref))
         assert max(errs) < tol, (case, n, depths, B, kind, dtype, need_gx, plan_tier(B, n, dtype), errs)
+
+
+@pytest.mark.parametrize("kind,tf", [("quanonet", True), ("heaqnn", False)])
+def test_fused_encoding_wide_latency_tier(cuda_device, kind, tf):
+    """n = 7 (fp32), small batch: the fused-encoding modes of the wide latency tier (frequency layers and their
+    gradients in-kernel) against the unfused path (torch frequency layers + x-given kernel + torch chain rule);
+    above the tier's batch limit the trainer must fall back to the unfused path by itself."""
+    from quanonet_b200.core.models_pt import HEAQNNPT, QuanONetPT
+    from quanonet_b200.train import DataParallelTrainer
+    dev, n, B = cuda_device, 7, 301
+    torch.manual_seed(21)
+    if kind == "quanonet":
+        mk = lambda: QuanONetPT(n, 9, 2, (3, 2, 2, 1), scale_coeff=0.3, if_trainable_freq=tf, ham_bound=(-2.0, 4.0))
+        inputs = (torch.randn(B, 9), torch.rand(B, 2))
+    else:
+        mk = lambda: HEAQNNPT(n, 10, (4, 2, 0, 0), scale_coeff=0.4, if_trainable_freq=tf)
+        inputs = (torch.randn(B, 10),)
+    y = torch.randn(B, 1)
+    ma = mk().to(dev)
+    if tf:
+        with torch.no_grad():
+            for mod in ma.modules():
+                if hasattr(mod, "weights") and hasattr(mod, "out_features"):
+                    mod.weights.uniform_(-0.5, 0.5)
+                    mod.bias.uniform_(-3, 3)
+    mb = mk().to(dev)
+    mb.load_state_dict(ma.state_dict())
+    ins = tuple(t.to(dev) for t in inputs)
+    yd = y.to(dev)
+    ta = DataParallelTrainer(ma, lr=1e-2, optimizer="sgd", use_fused_encoding=True)
+    tb = DataParallelTrainer(mb, lr=1e-2, optimizer="sgd", use_fused_encoding=False)
+    la = ta.compute_grads(ins, yd)
+    lb = tb.compute_grads(ins, yd)
+    assert ta._enc_by_batch == {B: True} and tb._enc_by_batch is None
+    assert abs(float(la) - float(lb)) <= 2e-5 * abs(float(lb))
+    assert rel_l2(ta.flat_grad.cpu().numpy(), tb.flat_grad.cpu().numpy()) < 2e-5
+    with torch.no_grad():
+        fused = ma(*ins)                  # fused inference path
+    with torch.enable_grad():
+        plain = ma(*ins)
+    assert rel_l2(fused.cpu().numpy(), plain.detach().cpu().numpy()) < 1e-5
+    big = tuple(t.repeat(20, 1) for t in ins)        # 6,020 samples: beyond the wide tier's limit for n = 7
+    ta.compute_grads(big, yd.repeat(20, 1))
+    assert ta._enc_by_batch[20 * B] is False
