@@ -115,3 +115,12 @@ def test_product_code_never_imports_the_oracle():
             if f.endswith(".py"):
                 src = open(os.path.join(dp, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), os.path.join(dp, f)
+
+
+def test_encoded_supported_static_rules():
+    """The size-independent part of the fused-encoding rule needs no device (the per-batch part asks the planner)."""
+    import torch
+    from quanonet_b200.ops import encoded_supported
+    assert encoded_supported(5, torch.float32) and encoded_supported(4, torch.float64)
+    assert not encoded_supported(5, torch.float64) and not encoded_supported(7, torch.float32)
+    assert not encoded_supported(7, torch.float64, batch=100) and not encoded_supported(10, torch.float32, batch=100)
