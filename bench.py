@@ -132,7 +132,23 @@ class ClockSampler:
                 "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
+# ---------------------------------------------------------------------------------- shared config
+def bench_config(world, B, fused=True, scaling="weak"):
+    """`config` of the JSON line — identical for the B200 arm and the reference arm."""
+    return {"workload": WORKLOAD, "num_qubits": N_QUBITS, "net_size": list(NET),
+            "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world}",
+            "l2_policy": "inputs larger than L2: 412 MB of (branch, trunk, target) per step vs 126 MB L2",
+            "step": ("ONE kernel: frequency layers + forward + MSE + adjoint-grad + batch reduction of all "
+                     "2,401 gradients; then all-reduce + Adam" if fused else
+                     "freq layers (torch) + fused fwd/MSE/adjoint-grad kernel + chain rule (torch) + "
+                     "all-reduce + Adam")}
+
+
 # ---------------------------------------------------------------------------------- CPU reference arm
+REF_BATCH = 1000          # bounded sample of the 1M-sample batch; the reference's own default is 100 (utils/common.py:128)
+REF_BATCH_SMALL = 100
+
+
 def cpu_reference_step_fn(B, threads=None):
     """One training step of the reference path on the host: frequency layers, TorchQuantum-faithful
     complex64 circuit with autograd (oracle/tq_faithful.py), MSELoss, backward, Adam."""
@@ -156,37 +172,38 @@ def cpu_reference_step_fn(B, threads=None):
     return step
 
 
-def time_cpu_reference(budget_s, steps=None, warmup=0):
-    """Returns (samples/s, ms/step, B, steps) of the CPU reference on a bounded sample."""
-    t0 = time.perf_counter()
-    cpu_reference_step_fn(64)()                      # calibration (also pages torch in)
-    rate = 64 / max(time.perf_counter() - t0, 1e-3)
-    n_steps = steps if steps is not None else 3
-    B = int(min(1000, max(32, rate * 2.5 * budget_s / (n_steps + warmup))))   # larger batches run ~2.5x faster/sample
+def time_cpu_reference(B, steps, warmup):
+    """(samples/s, ms/step) of the CPU reference: `steps` training steps of a FIXED batch of B samples."""
     step = cpu_reference_step_fn(B)
     for _ in range(warmup):
         step()
     t0 = time.perf_counter()
-    for _ in range(n_steps):
+    for _ in range(steps):
         step()
     dt = time.perf_counter() - t0
-    return B * n_steps / dt, dt / n_steps * 1e3, B, n_steps
+    return B * steps / dt, dt / steps * 1e3
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sps, ms, B, n_steps = time_cpu_reference(budget_s=120.0, steps=args.steps, warmup=args.warmup)
+    steps, warmup = max(1, args.steps), max(0, args.warmup)
+    sps, ms = time_cpu_reference(REF_BATCH, steps, warmup)
+    sps_small, ms_small = time_cpu_reference(REF_BATCH_SMALL, max(3, min(steps, 10)), 1)
     cores = torch.get_num_threads()
     line = {
         "impl": "reference", "metric": METRIC, "value": sps, "unit": "samples/s", "n_gpus": args.gpus,
-        "steps": n_steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "steps": steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "batch_per_step": B, "note": "bounded sample of the 1M-sample batch"},
+        "config": bench_config(max(1, args.gpus), args.batch),
         "cpu_baseline": {"value": sps, "unit": "samples/s", "cores": cores, "kind": "port",
-                         "sample": f"{n_steps} training steps of {B} samples (TorchQuantum-faithful complex64 "
-                                   f"restatement with autograd; torchquantum is not installable offline)"},
+                         "sample": f"{steps} training steps of a fixed {REF_BATCH}-sample slice of the batch "
+                                   f"(TorchQuantum-faithful complex64 restatement with autograd; torchquantum is "
+                                   f"not installable offline)",
+                         "batch_per_step": REF_BATCH,
+                         "reference_default_batch": {"batch_per_step": REF_BATCH_SMALL, "value": sps_small,
+                                                     "ms_per_step": ms_small}},
         "e2e": {"value": sps, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -213,18 +230,21 @@ def run_b200(args):
     B = args.batch
     K, W = args.steps, max(args.warmup, 3)
     f_fwd, f_all = alg_flops()
-
-    model = make_model(dev, seed=0)
-    trainer = DataParallelTrainer(model, lr=1e-3, optimizer="adam", use_fused_encoding=not args.unfused)
-    kernel_events = trainer.kernel_events = []
-    branch, trunk, y = synth_batch(B, seed=100 + rank, device=dev)
-    peak = fp32_peak_tflops(4000) if rank == 0 else None
+    sampler = ClockSampler(local)                 # NVML init + handle lookup happen HERE, before any timed region
+    align = torch.zeros(1, device=dev)
 
     def sync_all():
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
             torch.cuda.synchronize()
+
+    def aligned_start():
+        """barrier + synchronize, then a device-side rendezvous (a 1-float all-reduce the timed stream waits on)
+        so every rank's first timed kernel starts within microseconds of the others, whatever the host skew."""
+        sync_all()
+        if world > 1:
+            dist.all_reduce(align)
 
     def max_over_ranks(ms):
         if world == 1:
@@ -233,25 +253,68 @@ def run_b200(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    # ---- device-resident timing (value)
+    def timed_steps(trainer, data, n_steps, gB=None):
+        """n_steps training steps with an event after every step.  Returns (total ms max over ranks, total ms of
+        the fastest rank, per-step trace dict, last loss)."""
+        (branch, trunk), y = data
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(n_steps + 1)]
+        aligned_start()
+        evs[0].record()
+        for i in range(n_steps):
+            loss = trainer.step((branch, trunk), y, gB)
+            evs[i + 1].record()
+        sync_all()
+        total = evs[0].elapsed_time(evs[-1])
+        per = torch.tensor([evs[i].elapsed_time(evs[i + 1]) for i in range(n_steps)], device=dev, dtype=torch.float64)
+        if world > 1:
+            allper = [torch.empty_like(per) for _ in range(world)]
+            dist.all_gather(allper, per)
+            allper = torch.stack(allper)            # (world, steps)
+        else:
+            allper = per[None]
+        step_max, step_min = allper.max(0).values, allper.min(0).values
+        trace = {"first_step_ms_max": float(step_max[0]), "first_step_ms_min": float(step_min[0]),
+                 "later_steps_ms_max_mean": float(step_max[1:].mean()) if n_steps > 1 else None,
+                 "later_steps_ms_min_mean": float(step_min[1:].mean()) if n_steps > 1 else None,
+                 "rank_total_ms": [float(v) for v in allper.sum(1)]}
+        return max_over_ranks(total), -max_over_ranks(-total), trace, loss
+
+    # ---- device-resident timing (value): weak scaling, B samples per GPU
+    model = make_model(dev, seed=0)
+    trainer = DataParallelTrainer(model, lr=1e-3, optimizer="adam", use_fused_encoding=not args.unfused)
+    kernel_events = trainer.kernel_events = []
+    branch, trunk, y = synth_batch(B, seed=100 + rank, device=dev)
+    peak = fp32_peak_tflops(4000) if rank == 0 else None
     for _ in range(W):
         trainer.step((branch, trunk), y)
     kernel_events.clear()
-    sync_all()
-    sampler = ClockSampler(local)
     with sampler:
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(K):
-            loss = trainer.step((branch, trunk), y)
-        e1.record()
-        sync_all()
-    ms_local = e0.elapsed_time(e1)
-    ms_total = max_over_ranks(ms_local)
-    ms_min = -max_over_ranks(-ms_local)          # fastest rank: the spread shows stragglers
+        ms_total, ms_min, trace, loss = timed_steps(trainer, ((branch, trunk), y), K)
     ms_step = ms_total / K
     value = world * B * K / (ms_total * 1e-3)
     final_loss = float(loss)
+
+    # ---- replicas stay identical; the fused finalize+exchange kernel agrees with NCCL (N > 1)
+    replica_check = None
+    if world > 1:
+        flat = trainer.flat_param.detach().clone()
+        gathered = [torch.empty_like(flat) for _ in range(world)]
+        dist.all_gather(gathered, flat)
+        same = all(bool(torch.equal(g.view(torch.int32), gathered[0].view(torch.int32))) for g in gathered)
+        replica_check = {"params_bit_identical_across_ranks": same, "n_params": int(flat.numel())}
+        saved_ar, saved_fx = trainer._all_reduce, trainer._fused_exchange
+        trainer.compute_grads((branch, trunk), y)
+        g_lib = trainer.flat_grad.detach().clone()
+        trainer._fused_exchange = False
+        trainer._all_reduce = lambda t: dist.all_reduce(t)
+        trainer.compute_grads((branch, trunk), y)
+        g_nccl = trainer.flat_grad.detach().clone()
+        trainer._all_reduce, trainer._fused_exchange = saved_ar, saved_fx
+        rel = float((g_lib - g_nccl).norm() / g_nccl.norm())
+        replica_check.update({"exchange": "fused finalize+exchange kernel" if saved_fx else type(saved_ar).__name__,
+                              "grad_rel_diff_vs_nccl_allreduce": max_over_ranks(rel)})
+        torch.cuda.synchronize()
+
     if getattr(trainer, "_fused_exchange", False):
         # N > 1: the finalize kernel of the timed steps also waits for the peers (fused exchange), so its events
         # include rank skew.  For the roofline, time the compute kernels alone on a few extra, untimed steps.
@@ -262,6 +325,19 @@ def run_b200(args):
         sync_all()
         trainer._fused_exchange = True
     kern_ms = float(np.mean([a.elapsed_time(b) for a, b in kernel_events]))
+    trainer.kernel_events = None
+
+    # ---- strong scaling (BASELINE config 3): the SAME global batch of `B` samples sharded B/N per GPU
+    strong = None
+    if world > 1:
+        Bs = B // world
+        sdata = ((branch[:Bs], trunk[:Bs]), y[:Bs])
+        for _ in range(W):
+            trainer.step(*sdata, Bs * world)
+        s_total, s_min, s_trace, _ = timed_steps(trainer, sdata, K, Bs * world)
+        strong = {"scaling": "strong", "global_batch": Bs * world, "batch_per_gpu": Bs, "ms_per_step": s_total / K,
+                  "ms_per_step_fastest_rank": s_min / K, "value": Bs * world * K / (s_total * 1e-3),
+                  "unit": "samples/s", "per_step": s_trace}
 
     # ---- forward-only throughput (inference path), same batch
     with torch.no_grad():
@@ -301,7 +377,6 @@ def run_b200(args):
         for c in consumed:
             c.record(cur)
         enqueue_copy(0)
-        last = None
         for i in range(n_steps):
             if i + 1 < n_steps:
                 enqueue_copy(i + 1)
@@ -311,19 +386,22 @@ def run_b200(args):
             l = trainer.step((b_, t_), y_)
             consumed[slot].record(cur)
             loss_host.copy_(l.reshape(1).float(), non_blocking=True)     # D2H read of the step's loss
-            last = l
         torch.cuda.synchronize()
         return float(loss_host[0])
 
     e2e_loop(3)
-    sync_all()
-    t0 = time.perf_counter()
+    aligned_start()
     g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
     g0.record()
     e2e_loop(K)
     g1.record()
-    sync_all()
-    e2e_ms = max_over_ranks(max(g0.elapsed_time(g1), (time.perf_counter() - t0) * 1e3 * 0.0))
+    torch.cuda.synchronize()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    if world > 1:
+        dist.barrier()
+    # the slower of the device clock and the host clock around the same K steps, max over ranks
+    e2e_ms = max_over_ranks(max(g0.elapsed_time(g1), wall_ms))
     e2e_value = world * B * K / (e2e_ms * 1e-3)
     h2d = sum(t.numel() * t.element_size() for t in host[0])
 
@@ -335,7 +413,7 @@ def run_b200(args):
     sb, st_, sy = synth_batch(sB, seed=300 + rank, device=dev)
     for _ in range(5):
         small_tr.step((sb, st_), sy)
-    sync_all()
+    aligned_start()
     s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     s0.record()
     for _ in range(50):
@@ -361,10 +439,11 @@ def run_b200(args):
 
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        sps, ms, Bc, ns = time_cpu_reference(budget_s=20.0)
+        sps, ms = time_cpu_reference(REF_BATCH, 5, 1)
         cpu_base = {"value": sps, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
-                    "sample": f"{ns} training steps of {Bc} samples of the same workload "
-                              f"(TorchQuantum-faithful complex64 restatement, autograd backward)"}
+                    "sample": f"5 training steps of a fixed {REF_BATCH}-sample slice of the same workload "
+                              f"(TorchQuantum-faithful complex64 restatement, autograd backward)",
+                    "batch_per_step": REF_BATCH, "ms_per_step": ms}
 
     if rank == 0:
         achieved = f_all * B / (kern_ms * 1e-3) / 1e12
@@ -381,16 +460,10 @@ def run_b200(args):
             "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_step, "ms_per_step_fastest_rank": ms_min / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "num_qubits": N_QUBITS, "net_size": list(NET),
-                       "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world}",
-                       "l2_policy": "inputs larger than L2: 412 MB of (branch, trunk, target) per step vs 126 MB L2",
-                       "step": ("ONE kernel: frequency layers + forward + MSE + adjoint-grad + batch reduction of all "
-                                "2,401 gradients; then all-reduce + Adam" if trainer.fused_encoding else
-                                "freq layers (torch) + fused fwd/MSE/adjoint-grad kernel + chain rule (torch) + "
-                                "all-reduce + Adam")},
+            "config": bench_config(world, B, trainer.fused_encoding),
             "clocks": sampler.summary(),
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
-                    "ms_per_step": e2e_ms / K},
+                    "ms_per_step": e2e_ms / K, "timer": "max(CUDA events, host wall clock) over the K steps, max over ranks"},
             # this library's kernels per step: prep, circuit kernel, finalize (+ finalize_enc) — with N > 1 the
             # finalize kernel is also the all-reduce (finalize_exchange_kernel), else one peer all-reduce kernel more
             "gpu_launches": (3 if getattr(trainer, "_fused_exchange", False) else
@@ -402,11 +475,16 @@ def run_b200(args):
                          "flops_per_sample": f_all, "peak_source": "FFMA probe measured on this GPU in this run "
                          "(MEASURED_PEAKS.json has no FP32 entry)", "peak_nominal": nominal,
                          "frac_of_nominal": achieved / nominal},
+            "per_step": trace,
             "forward_only": {"value": B / (fwd_ms * 1e-3), "unit": "samples/s",
                              "tflops": f_fwd * B / (fwd_ms * 1e-3) / 1e12},
             "small_batch": small,
             "final_loss": final_loss,
         }
+        if strong is not None:
+            line["strong_scaling"] = strong
+        if replica_check is not None:
+            line["replica_check"] = replica_check
         if cpu_base is not None:
             line["cpu_baseline"] = cpu_base
         print(json.dumps(line), flush=True)

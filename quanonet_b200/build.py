@@ -17,7 +17,7 @@ CSRC = os.path.join(PKG_DIR, "csrc")
 BUILD_DIR = os.path.join(PKG_DIR, "_build")
 LIB_PATH = os.path.join(PKG_DIR, "libquanonet_b200.so")
 
-SOURCES = ["hea_reg_f64.cu", "hea_reg_f32_lanes.cu", "hea_reg_f32.cu", "hea_smem.cu", "hea_hbm.cu", "hea_warp.cu", "hea_generic.cu", "qon_capi.cu"]
+SOURCES = ["hea_reg_f64.cu", "hea_reg_f32_lanes.cu", "hea_reg_f32.cu", "hea_smem.cu", "hea_hbm.cu", "hea_warp.cu", "hea_tc.cu", "hea_generic.cu", "qon_capi.cu"]
 NVCC_FLAGS = [
     "-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
     "-Xcompiler", "-fPIC", "-Xptxas", "-v",

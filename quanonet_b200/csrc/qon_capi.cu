@@ -30,6 +30,17 @@ int fail(int code, const char* fmt, ...) {
 
 constexpr int kMaxQubits = 24;
 
+// Tensor-core tier switch (hea_tc.cuh): QON_TC=0/1 in the environment, or qon_tc_config() at run time.
+struct TcConfig { int enable; float* dbg; int* err; int64_t min_batch; };
+TcConfig& tc_config() {
+    static TcConfig c = [] {
+        const char* e = getenv("QON_TC");
+        const char* m = getenv("QON_TC_MIN_B");
+        return TcConfig{e ? atoi(e) : 0, nullptr, nullptr, m ? (int64_t)atoll(m) : (int64_t)16384};
+    }();
+    return c;
+}
+
 // ---------------------------------------------------------------------------------------------
 // prep: per-(sublayer, qubit) gate tables, Hamiltonian diagonal, depth array, column -> source-row
 // index table of the fused encoding, zeroed partial sums
@@ -404,7 +415,7 @@ struct Plan {
     bool fast_hbm = false;    // tier 2 served by hea_hbm.cuh (fp32) instead of the generic kernel
     WarpPlan wp{};
     bool fast_warp = false;   // tier 0 served by hea_warp.cuh (one amplitude per lane, small batches)
-    size_t off_u = 0, off_r = 0, off_h = 0, off_d = 0, off_i = 0, off_m = 0, off_state = 0, total = 0;
+    size_t off_u = 0, off_r = 0, off_h = 0, off_d = 0, off_i = 0, off_m = 0, off_state = 0, off_tc = 0, total = 0;
     int64_t rowlen = 0, mpart_len = 0;
 };
 
@@ -536,6 +547,8 @@ int make_plan(int64_t B, int n, int K, const int* depth, int dtype, int mode, Pl
     pl->off_state = off;
     if (pl->fast_hbm) off = align_up(off + pl->hp.bytes);
     else if (pl->tier == 2) off = align_up(off + (size_t)pl->grid * (grad ? 4 : 2) * ((size_t)1 << n) * es);
+    pl->off_tc = off;
+    if (dtype == QON_F32 && n == 5) off = align_up(off + tc_workspace_bytes(K));   // tensor-core tier: block matrices
     pl->total = off;
     return 0;
 }
@@ -632,7 +645,18 @@ int run(const Job& j) {
     }
     if (j.B > 0) {
         cudaError_t e;
-        if (pl.fast_warp) {
+        const TcConfig& tcc = tc_config();
+        bool use_tc = false;
+        if constexpr (sizeof(T) == 4)
+            use_tc = tcc.enable && n == 5 && (mode == 0 || mode == 3) && j.ham_kind == QON_HAM_DIAG && j.B >= tcc.min_batch;
+        if (use_tc) {
+            if constexpr (sizeof(T) == 4) {
+                int dev; DeviceInfo di;
+                if (!device_info(&dev, &di)) return fail(QON_ERR_NO_DEVICE, "no usable CUDA device");
+                e = tc_forward_launch(mode, di.sms, (const HeaParams<float>&)p, (const float*)j.w, dp, base + pl.off_tc,
+                                      tcc.dbg, tcc.err, st);
+            } else e = cudaErrorInvalidValue;
+        } else if (pl.fast_warp) {
             if constexpr (sizeof(T) == 4) e = warp_launch_f32(n, mode, pl.grid, pl.wp, (const HeaParams<float>&)p, dp, st);
             else e = warp_launch_f64(n, mode, pl.grid, pl.wp, (const HeaParams<double>&)p, dp, st);
         } else if (pl.tier == 0) {
@@ -869,6 +893,14 @@ int qon_encoded_mse_step_dp(const void* u0, int64_t ldu0, int in0, int K0, const
     }
     j.world = world; j.rank = rank; j.peer_max_len = max_len;
     return dispatch(j);
+}
+
+void qon_tc_config(int enable, void* dbg, void* err, int64_t min_batch) {
+    TcConfig& c = tc_config();
+    c.enable = enable;
+    c.dbg = (float*)dbg;
+    c.err = (int*)err;
+    if (min_batch >= 0) c.min_batch = min_batch;
 }
 
 double qon_measure_fp32_peak_tflops(int iters, void* stream) {
