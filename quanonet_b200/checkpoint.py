@@ -195,30 +195,73 @@ def ms_npz_to_pt_state_dict(path, net_size=(40, 2, 20, 2), num_qubits=5, if_trai
     return {k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in arrays.items()}
 
 
-_DIR_RE = re.compile(
-    r"(?P<op>[A-Za-z]+)_(?P<model>QuanONet|HEAQNN)_Net(?P<net>[\d-]+)_Q(?P<q>\d+)"
-    r"(?P<tf>_TF)?_S(?P<scale>[\d.eE+-]+)_(?P<ntrain>\d+)x(?P<npts>\d+)_Seed(?P<seed>\d+)")
+# One independent pattern per field, the way the reference reads its own directory names (infer.py:60-86);
+# the names are written by utils/logger.py:55-118:
+#   <Op>_<Model>_Net<a-b[-c-d]>_Q<n>_<TF|FF>_S<scale>[_Pauli<P>][_Diag<v-v-..>|_Ham<lb-ub>][_<TQ|Qiskit|PL>]_<N>x<P>_Seed<k>
+_MODEL_RE = re.compile(r"(?:^|_)(QuanONet|HEAQNN)(?:_|$)")
+_OP_RE = re.compile(r"^([A-Za-z0-9]+?)_(?:QuanONet|HEAQNN)(?:_|$)")
+_NET_RE = re.compile(r"_Net(\d+(?:-\d+)*)(?:_|$)")
+_Q_RE = re.compile(r"_Q(\d+)(?:_|$)")
+_TF_RE = re.compile(r"_(TF|FF)(?:_|$)")
+_S_RE = re.compile(r"_S(\d[\d.]*(?:[eE][+-]?\d+)?)(?:_|$)")
+_PAULI_RE = re.compile(r"_Pauli([XYZ])(?:_|$)")
+_NUM = r"-?\d[\d.]*(?:[eE][+-]?\d+)?"
+_DIAG_RE = re.compile(r"_Diag(" + _NUM + r"(?:-" + _NUM + r")*)(?:_|$)")
+_HAM_RE = re.compile(r"_Ham(" + _NUM + r")-(" + _NUM + r")(?:_|$)")
+_QB_RE = re.compile(r"_(TQ|Qiskit|PL)(?:_|$)")
+_DATA_RE = re.compile(r"_(\d+)x(\d+)_Seed(\d+)(?:_|$)")
+_QB_MAP = {"TQ": "torchquantum", "Qiskit": "qiskit", "PL": "pennylane"}
+
+
+def _split_signed(text: str):
+    """'-5--2.5-2.5-5' -> [-5.0, -2.5, 2.5, 5.0]: values joined by '-' (utils/logger.py:95), negatives included.
+    A '-' that follows a digit is the separator; any other '-' is a sign."""
+    return [float(v) for v in re.findall(_NUM, re.sub(r"(?<=[\d.])-", " ", text))]
 
 
 def parse_experiment_dir(path: str) -> dict:
     """Recover hyper-parameters from a reference experiment directory name such as
-    ``Advection_QuanONet_Net40-2-20-2_Q5_TF_S0.1_1000x100_Seed0`` (naming scheme:
-    ``utils/logger.py:55-118``; the reference's own parser is ``infer.py:60-86``)."""
-    m = None
+    ``Advection_QuanONet_Net40-2-20-2_Q5_TF_S0.1_1000x100_Seed0`` or
+    ``RDiffusion_HEAQNN_Net64-2_Q5_FF_S0.01_PauliX_Ham-1-1_TQ_1000x100_Seed3`` (naming scheme:
+    ``utils/logger.py:55-118``; the reference's own parser is ``infer.py:60-86``).  Fields the name does not
+    carry are absent from the result (``infer._resolve_config`` fills the reference's defaults, ``infer.py:47-57``);
+    ``if_trainable_freq`` is True for ``_TF`` and False for ``_FF``."""
+    name = None
     for part in reversed(os.path.normpath(path).split(os.sep)):
-        m = _DIR_RE.search(part)
-        if m:
+        if _MODEL_RE.search(part):
+            name = part
             break
-    if not m:
+    if name is None:
         raise ValueError(f"cannot parse experiment hyper-parameters from {path!r}")
-    return {
-        "operator": m["op"],
-        "model_type": m["model"],
-        "net_size": tuple(int(v) for v in m["net"].split("-")),
-        "num_qubits": int(m["q"]),
-        "if_trainable_freq": m["tf"] is not None,
-        "scale_coeff": float(m["scale"]),
-        "num_train": int(m["ntrain"]),
-        "num_points": int(m["npts"]),
-        "seed": int(m["seed"]),
-    }
+    cfg = {"model_type": _MODEL_RE.search(name).group(1)}
+    m = _OP_RE.search(name)
+    if m:
+        cfg["operator"] = m.group(1)
+    m = _NET_RE.search(name)
+    if m:
+        cfg["net_size"] = tuple(int(v) for v in m.group(1).split("-"))
+    m = _Q_RE.search(name)
+    if m:
+        cfg["num_qubits"] = int(m.group(1))
+    m = _TF_RE.search(name)
+    if m:
+        cfg["if_trainable_freq"] = m.group(1) == "TF"
+    m = _S_RE.search(name)
+    if m:
+        cfg["scale_coeff"] = float(m.group(1))
+    m = _PAULI_RE.search(name)
+    if m:
+        cfg["ham_pauli"] = m.group(1)
+    m = _DIAG_RE.search(name)
+    if m:
+        cfg["ham_diag"] = _split_signed(m.group(1))
+    m = _HAM_RE.search(name)
+    if m:
+        cfg["ham_bound"] = (float(m.group(1)), float(m.group(2)))
+    m = _QB_RE.search(name)
+    if m:
+        cfg["quantum_backend"] = _QB_MAP[m.group(1)]
+    m = _DATA_RE.search(name)
+    if m:
+        cfg["num_train"], cfg["num_points"], cfg["seed"] = int(m.group(1)), int(m.group(2)), int(m.group(3))
+    return cfg

@@ -68,9 +68,9 @@ HbmPlan hbm_plan(int64_t B, int n, int K, int mode);
 cudaError_t hbm_run(const HeaParams<float>& p, const int* depth_host, int n, int K, int mode, const HbmPlan& pl,
                     char* state_ws, cudaStream_t st);
 
-// fp32 tensor-core tier (hea_tc.cu): n = 5, diagonal observables; modes 0 / 3 (forward)
-size_t tc_workspace_bytes(int K);
-cudaError_t tc_forward_launch(int mode, int sms, const HeaParams<float>& p, const float* w, const DepthPack& dp,
-                              char* tc_ws, float* dbg, int* err_user, cudaStream_t st);
+// fp32 tensor-core tier (hea_tc.cu): n = 5, diagonal observables, every mode of hea_reg_inst.cuh
+size_t tc_workspace_bytes(int K, int S);
+cudaError_t tc_launch(int mode, int version, int sms, const HeaParams<float>& p, const float* w, const DepthPack& dp,
+                      char* tc_ws, float* dbg, int* err_user, cudaStream_t st);
 
 }  // namespace qon

@@ -32,7 +32,8 @@ constexpr int kTcStages = 4;
 constexpr int kTcImgBytes = 16384;             // per block: B_hi (8 KB) | B_lo (8 KB)
 constexpr int kTcThreads = 17 * 32;
 constexpr float kTcSA = 32768.f;               // state scale  (|amplitude| <= 1 -> f16 normal range)
-constexpr float kTcSB = 4096.f;                // matrix scale
+constexpr float kTcSB = 1.f;                   // matrix scale: 1 keeps a GEMM's output at the operand scale (lo parts of
+                                               // small entries are f16 subnormals: absolute error 2^-25, norm-relative 3e-8)
 
 // byte offset of element (nn, kk) of a 64 x 64 f16 operand stored K-major without swizzle:
 // core matrices of 8 rows x 16 bytes, K-adjacent core matrices 128 B apart (LBO), row groups 1024 B apart (SBO)

@@ -1,0 +1,591 @@
+// Tensor-core tier, second kernel: forward AND the one-kernel adjoint backward (n = 5, fp32 results).
+//
+// Forward as in hea_tc.cuh (block unitaries M_k = [H] W_k H as f16x3 GEMMs, RX layers as diagonal phases in
+// the Hadamard basis).  Reverse sweep (what loss.backward() at solvers/solver_pt.py:235 produces, by adjoint
+// differentiation): one GEMM per SUBLAYER un-applies it on psi and lam at once,
+//     G_s = [H if s is the first sublayer of its block] R_s^+ Ring^+ [H if the cut is held in the Hadamard basis],
+// so the registers always hold the pair (psi, lam) AFTER a sublayer's CNOT ring.  The three Pauli moments per qubit
+// that the finalize kernel turns into angle gradients are defined BEFORE the ring; CNOTs are Clifford, so they are
+// measured as Pauli strings T = Ring P_q Ring^+ (csrc/tc_strings.cuh, generated and verified by
+// scripts/gen_tc_strings.py; the whole sweep is emulated against the fp64 oracle in scripts/tc_emulate_bwd.py).
+// The gradient of an encoding angle is a Z-type (diagonal) moment in the Hadamard basis, taken right after the
+// GEMM of a block's first sublayer, before the conjugate phases are applied.
+//
+// Roles in a CTA (1 per SM): NT tiles of 128 samples (NT = 4 forward-only, 2 with gradients); tile t is owned by
+// compute warps 4t..4t+3 (thread = sample = TMEM lane) and by MMA warp 4*NT + t, whose elected thread streams the
+// step's B image through a private ring (1-D bulk async copies) and issues the tcgen05.mma's.  Hand-offs are
+// mbarriers only: a_ready[t] (compute -> MMA: "A operand written"), d_ready[t] (tcgen05.commit: "D complete").
+#pragma once
+#include "hea_reg.cuh"
+#include "hea_tc.cuh"
+#include "tc_strings.cuh"
+
+namespace qon {
+
+template <bool GRAD> struct TcGeom {
+    static constexpr int NT = GRAD ? 2 : 4;                 // tiles per CTA
+    static constexpr int NS = GRAD ? 4 : 3;                 // B-image ring stages per tile
+    static constexpr int COMPUTE_WARPS = 4 * NT;
+    static constexpr int WARPS = COMPUTE_WARPS + 4;         // + one warpgroup hosting the NT MMA warps
+    static constexpr int THREADS = WARPS * 32;
+    static constexpr int TILE_COLS = GRAD ? 256 : 128;      // TMEM columns per tile
+    static constexpr int SMEM = NT * NS * kTcImgBytes;
+};
+
+// a (.) P(z) + c with the operand patterns of ffma2.cuh applied to the packed operand z
+#define QON_P2V_DECL ".reg .b64 pb; .reg .f32 zx, zy, tx, ty; mov.b64 {zx, zy}, %2; "
+#define QON_FMA2VP_CASE(N)                                                                             \
+    if constexpr (PAT == N)                                                                            \
+        asm("{ " QON_P2V_DECL QON_P2_##N "fma.rn.f32x2 %0, pb, %1, %3; }" : "=l"(d) : "l"(a), "l"(z), "l"(c));
+template <int PAT>
+__device__ __forceinline__ u64 fma2_vp(u64 a, u64 z, u64 c) {
+    u64 d;
+    QON_FMA2VP_CASE(0) QON_FMA2VP_CASE(2) QON_FMA2VP_CASE(3) QON_FMA2VP_CASE(6)
+    return d;
+}
+
+__host__ __device__ constexpr bool tc_parity(int v) { return ((v ^ (v >> 1) ^ (v >> 2) ^ (v >> 3) ^ (v >> 4)) & 1) != 0; }
+
+__device__ __forceinline__ u64 tc_pair(const uint32_t (&r)[64], int z) {
+    return pack2(__uint_as_float(r[2 * z]), __uint_as_float(r[2 * z + 1]));
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// prep of the reverse images: grid = S CTAs of 32 threads, image s' = S-1-s (execution order of the sweep)
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32) tc_prep_rev_kernel(const float* __restrict__ w, int K, int S, DepthPack dp,
+                                                         unsigned char* __restrict__ rimg) {
+    constexpr int n = 5, N = 32;
+    __shared__ double vr[N][N + 1], vi[N][N + 1];
+    const int s = blockIdx.x, j = threadIdx.x;
+    int k = 0, s0 = 0;
+    while (s0 + dp.d[k] <= s) { s0 += dp.d[k]; ++k; }
+    const bool first_in_block = s == s0;
+    const bool input_had = (s == s0 + dp.d[k] - 1) && (k < K - 1);
+    const double h = 0.70710678118654752440;
+    auto fwht = [&]() {
+        for (int q = 0; q < n; ++q)
+            for (int z = 0; z < N; ++z) {
+                if (z & (1 << q)) continue;
+                const int z1 = z | (1 << q);
+                const double x0r = vr[z][j], x0i = vi[z][j], x1r = vr[z1][j], x1i = vi[z1][j];
+                vr[z][j] = h * (x0r + x1r); vi[z][j] = h * (x0i + x1i);
+                vr[z1][j] = h * (x0r - x1r); vi[z1][j] = h * (x0i - x1i);
+            }
+    };
+    for (int z = 0; z < N; ++z) { vr[z][j] = z == j ? 1.0 : 0.0; vi[z][j] = 0.0; }
+    if (input_had) fwht();
+    for (int i = n - 1; i >= 0; --i) {   // Ring^+ : the CNOTs in reverse order
+        const int c = (i + 1) % n;
+        for (int z = 0; z < N; ++z) {
+            if (((z >> c) & 1) && !((z >> i) & 1)) {
+                const int z1 = z | (1 << i);
+                double t = vr[z][j]; vr[z][j] = vr[z1][j]; vr[z1][j] = t;
+                t = vi[z][j]; vi[z][j] = vi[z1][j]; vi[z1][j] = t;
+            }
+        }
+    }
+    for (int q = 0; q < n; ++q) {
+        const double a = (double)w[((int64_t)s * 3 + 0) * n + q];
+        const double b = (double)w[((int64_t)s * 3 + 1) * n + q];
+        const double c = (double)w[((int64_t)s * 3 + 2) * n + q];
+        double sa, ca, sb, cb, sc, cc;
+        sincos(0.5 * a, &sa, &ca);
+        sincos(0.5 * b, &sb, &cb);
+        sincos(0.5 * c, &sc, &cc);
+        const double ar = cb * (cc * ca - sc * sa), ai = -sb * (cc * ca + sc * sa);
+        const double br = cb * (sc * ca + cc * sa), bi = sb * (cc * sa - sc * ca);
+        // U^+ = [[conj(al), conj(be)], [-be, al]]
+        for (int z = 0; z < N; ++z) {
+            if (z & (1 << q)) continue;
+            const int z1 = z | (1 << q);
+            const double x0r = vr[z][j], x0i = vi[z][j], x1r = vr[z1][j], x1i = vi[z1][j];
+            vr[z][j] = ar * x0r + ai * x0i + br * x1r + bi * x1i;
+            vi[z][j] = ar * x0i - ai * x0r + br * x1i - bi * x1r;
+            vr[z1][j] = -br * x0r + bi * x0i + ar * x1r - ai * x1i;
+            vi[z1][j] = -br * x0i - bi * x0r + ar * x1i + ai * x1r;
+        }
+    }
+    if (first_in_block) fwht();
+    __half* hi = reinterpret_cast<__half*>(rimg + (size_t)(S - 1 - s) * kTcImgBytes);
+    __half* lo = hi + 4096;
+    auto put = [&](int nn, int kk, double v) {
+        const double vs = v * (double)kTcSB;
+        const __half hh = __double2half(vs);
+        const __half ll = __double2half(vs - (double)__half2float(hh));
+        const int o = tc_b_offset(nn, kk) >> 1;
+        hi[o] = hh;
+        lo[o] = ll;
+    };
+    for (int i = 0; i < N; ++i) {
+        const double re = vr[i][j], im = vi[i][j];
+        put(2 * i, 2 * j, re);
+        put(2 * i, 2 * j + 1, -im);
+        put(2 * i + 1, 2 * j, im);
+        put(2 * i + 1, 2 * j + 1, re);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// device helpers
+// ---------------------------------------------------------------------------------------------------------
+// whole D row (64 f32 columns) -> registers
+__device__ __forceinline__ void tc_load_state(uint32_t taddr, uint32_t (&r)[64]) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        uint32_t t[16];
+        tc::tmem_ld16(taddr + 16u * c, t);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) r[16 * c + i] = t[i];
+    }
+    tc::tmem_wait_ld();
+}
+
+// registers (scaled state) -> f16 hi | lo operand rows at taddr (+0: hi, +32: lo)
+__device__ __forceinline__ void tc_store_operand(uint32_t taddr, const uint32_t (&r)[64]) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        uint32_t ahi[8], alo[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float xr = __uint_as_float(r[16 * c + 2 * i]), xi = __uint_as_float(r[16 * c + 2 * i + 1]);
+            const float hr = __uint_as_float(r[16 * c + 2 * i] & 0xFFFFE000u);
+            const float hi_ = __uint_as_float(r[16 * c + 2 * i + 1] & 0xFFFFE000u);
+            ahi[i] = tc::cvt_f16x2(hr, hi_);
+            alo[i] = tc::cvt_f16x2(xr - hr, xi - hi_);
+        }
+        tc::tmem_st8(taddr + 8u * c, ahi);
+        tc::tmem_st8(taddr + 32u + 8u * c, alo);
+    }
+}
+
+// r <- scale-folded phases (.) r   (CONJ: conjugate phases)
+template <bool CONJ>
+__device__ __forceinline__ void tc_apply_phases(uint32_t (&r)[64], const float (&pr)[16], const float (&pi)[16]) {
+#pragma unroll
+    for (int z = 0; z < 32; ++z) {
+        const u64 v = tc_pair(r, z);
+        const int t = z < 16 ? z : 31 - z;
+        const bool cj = (z >= 16) != CONJ;     // p[31 - z] = conj(p[z])
+        u64 nv = mul2<0>(pr[t], v);
+        nv = cj ? fma2<3>(pi[t], v, nv) : fma2<2>(pi[t], v, nv);
+        float xr, xi;
+        unpack2(nv, xr, xi);
+        r[2 * z] = __float_as_uint(xr);
+        r[2 * z + 1] = __float_as_uint(xi);
+    }
+}
+
+// Im <lam| T |psi> for the 15 strings of one cut type: mv[3q + {0,1,2}] = {X,Y,Z}_q moments
+template <bool HAD>
+__device__ __forceinline__ void tc_moments(const uint32_t (&ps)[64], const uint32_t (&lm)[64], float (&mv)[16]) {
+    static_for<15>([&](auto Tc) {
+        constexpr int T = decltype(Tc)::value;
+        constexpr TcString st = HAD ? kTcStrHad[T] : kTcStrComp[T];
+        u64 acc0 = 0ull, acc1 = 0ull;
+        static_for<32>([&](auto Zc) {
+            constexpr int zp = decltype(Zc)::value;
+            constexpr bool neg = tc_parity((zp ^ st.mx) & st.mz);
+            // Im(i^k s c), c = conj(lam_zp) psi_{zp^mx}:  k=0: s Im c | 1: s Re c | 2: -s Im c | 3: -s Re c
+            constexpr bool want_re = (st.k & 1) != 0;
+            constexpr bool minus = neg != (st.k >= 2);
+            constexpr int PAT = want_re ? (minus ? 6 : 0) : (minus ? 2 : 3);
+            const u64 l = tc_pair(lm, zp), pp = tc_pair(ps, zp ^ st.mx);
+            if constexpr (zp & 1) acc1 = fma2_vp<PAT>(l, pp, acc1);
+            else acc0 = fma2_vp<PAT>(l, pp, acc0);
+        });
+        mv[T] = (lo2(acc0) + hi2(acc0)) + (lo2(acc1) + hi2(acc1));
+    });
+    mv[15] = 0.f;
+}
+
+// encoding-angle gradients: sum_z (1 - 2 z_q) Im(conj(mu_z) phi_z), q = 0..4
+__device__ __forceinline__ void tc_xgrad(const uint32_t (&ps)[64], const uint32_t (&lm)[64], float (&gq)[5]) {
+    static_for<5>([&](auto Qc) {
+        constexpr int q = decltype(Qc)::value;
+        u64 acc0 = 0ull, acc1 = 0ull;
+        static_for<32>([&](auto Zc) {
+            constexpr int z = decltype(Zc)::value;
+            constexpr bool neg = ((z >> q) & 1) != 0;
+            const u64 l = tc_pair(lm, z), pp = tc_pair(ps, z);
+            if constexpr (z & 1) acc1 = neg ? fma2_vp<2>(l, pp, acc1) : fma2_vp<3>(l, pp, acc1);
+            else acc0 = neg ? fma2_vp<2>(l, pp, acc0) : fma2_vp<3>(l, pp, acc0);
+        });
+        gq[q] = (lo2(acc0) + hi2(acc0)) + (lo2(acc1) + hi2(acc1));
+    });
+}
+
+// bounded mbarrier wait without busy work: try_wait suspends in hardware for up to ~20 us per probe
+__device__ __forceinline__ bool tc_wait(uint32_t bar, uint32_t parity, int* err) {
+    for (int it = 0; it < 100000; ++it) {
+        uint32_t ok;
+        asm volatile(
+            "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3; selp.u32 %0, 1, 0, p; }"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity), "r"(20000u)
+            : "memory");
+        if (ok) return true;
+        if ((it & 63) == 63 && *reinterpret_cast<volatile int*>(err) != 0) break;
+    }
+    atomicExch(err, 1);
+    return false;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// the kernel.  ENC as in hea_reg.cuh (0: x given, 1: fused encoding, 2: + frequency-layer gradients)
+// images: [K forward block images | S reverse sublayer images in sweep order]
+// ---------------------------------------------------------------------------------------------------------
+template <bool GRAD, bool NEED_GX, int ENC, bool DBG>
+__global__ void __launch_bounds__(TcGeom<GRAD>::THREADS, 1)
+hea_tc_kernel(const HeaParams<float> p, const unsigned char* __restrict__ images, float* dbg, int* err) {
+    using G = TcGeom<GRAD>;
+    constexpr int NQ = 5, NT = G::NT, NS = G::NS;
+    constexpr bool FREQ_GRAD = GRAD && ENC == 2;
+    constexpr bool WANT_GX = NEED_GX || FREQ_GRAD;
+    static_assert(!(NEED_GX && ENC != 0), "grad_x is only materialised when x is");
+    extern __shared__ __align__(1024) unsigned char tc_smem[];
+    __shared__ __align__(8) uint64_t bar_full[NT][NS], bar_a[NT], bar_d[NT];
+    __shared__ uint32_t tmem_base_s;
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t ntiles = (p.B + 127) / 128;
+    const int64_t rounds = (ntiles + (int64_t)gridDim.x * NT - 1) / ((int64_t)gridDim.x * NT);
+    const int nsteps = p.K + (GRAD ? p.S : 0);
+
+    if (threadIdx.x == 0) {
+        for (int t = 0; t < NT; ++t) {
+            for (int i = 0; i < NS; ++i) tc::mbar_init(tc::smem_u32(&bar_full[t][i]), 1);
+            tc::mbar_init(tc::smem_u32(&bar_a[t]), 4);
+            tc::mbar_init(tc::smem_u32(&bar_d[t]), 1);
+        }
+        tc::mbar_fence_init();
+    }
+    if (warp == G::COMPUTE_WARPS) tc::tmem_alloc512(tc::smem_u32(&tmem_base_s));
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+
+    if (warp >= G::COMPUTE_WARPS) {
+        // =================================================== MMA warps: one elected thread per tile
+        if constexpr (GRAD) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");   // hand registers to the compute warps
+        const int t = warp - G::COMPUTE_WARPS;
+        if (t < NT && lane == 0) {
+            const uint32_t mD = tmem_base + (uint32_t)t * G::TILE_COLS;
+            const uint32_t mA = mD + (GRAD ? 128u : 64u);
+            const uint32_t ring = tc::smem_u32(tc_smem + (size_t)t * NS * kTcImgBytes);
+            const uint32_t bar_a_t = tc::smem_u32(&bar_a[t]), bar_d_t = tc::smem_u32(&bar_d[t]);
+            constexpr uint32_t idesc = tc::idesc_f16(128, 64);
+            const int64_t total = rounds * nsteps;
+            auto fetch = [&](int64_t g) {
+                const int stage = (int)(g % NS);
+                const uint32_t fb = tc::smem_u32(&bar_full[t][stage]);
+                tc::mbar_expect_tx(fb, kTcImgBytes);
+                tc::bulk_g2s(ring + (uint32_t)stage * kTcImgBytes, images + (size_t)(g % nsteps) * kTcImgBytes, kTcImgBytes, fb);
+            };
+            for (int64_t g = 0; g < NS - 1 && g < total; ++g) fetch(g);
+            bool dead = false;
+            for (int64_t g = 0; g < total; ++g) {
+                const int stage = (int)(g % NS);
+                const bool rev = GRAD && (int)(g % nsteps) >= p.K;
+                if (!dead && !tc_wait(bar_a_t, (uint32_t)(g & 1), err)) dead = true;
+                tc::tc_fence_after();
+                if (!dead && !tc_wait(tc::smem_u32(&bar_full[t][stage]), (uint32_t)((g / NS) & 1), err)) dead = true;
+                const uint32_t sb = ring + (uint32_t)stage * kTcImgBytes;
+                if (!dead) {
+                    const int nstate = rev ? 2 : 1;
+                    for (int v = 0; v < nstate; ++v) {
+                        const uint32_t d = mD + 64u * v, a = mA + 64u * v;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            tc::mma_f16_ts(d, a + 8u * j, tc::smem_desc_kmajor(sb + 256u * j, 128u, 1024u), idesc, j > 0);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            tc::mma_f16_ts(d, a + 8u * j, tc::smem_desc_kmajor(sb + 8192u + 256u * j, 128u, 1024u), idesc, 1u);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            tc::mma_f16_ts(d, a + 32u + 8u * j, tc::smem_desc_kmajor(sb + 256u * j, 128u, 1024u), idesc, 1u);
+                    }
+                }
+                tc::mma_commit(bar_d_t);
+                // the stage of step g-1 is free: its MMAs completed before a_ready(g) could be signalled
+                if (g + NS - 1 < total) fetch(g + NS - 1);
+            }
+        }
+        __syncwarp();
+    } else {
+        // =================================================== compute warps
+        if constexpr (GRAD) asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");  // 168*384 = 232*256 + 40*128
+        const int t = warp >> 2, quarter = warp & 3;
+        const uint32_t lane_sel = (uint32_t)(quarter * 32) << 16;
+        const uint32_t tDp = tmem_base + lane_sel + (uint32_t)t * G::TILE_COLS;     // D psi
+        const uint32_t tDl = tDp + 64u;                                              // D lam      (GRAD)
+        const uint32_t tAp = tDp + (GRAD ? 128u : 64u);                              // A psi: hi 32 | lo 32
+        const uint32_t tAl = tAp + 64u;                                              // A lam      (GRAD)
+        const uint32_t bar_a_t = tc::smem_u32(&bar_a[t]), bar_d_t = tc::smem_u32(&bar_d[t]);
+        uint32_t dpar = 0;
+        bool dead = false;
+        auto wait_d = [&]() {
+            if (!dead && !tc_wait(bar_d_t, dpar, err)) dead = true;
+            dpar ^= 1u;
+            tc::tc_fence_after();
+        };
+        auto signal_a = [&]() {
+            tc::tmem_wait_st();
+            tc::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(bar_a_t);
+        };
+        float hmax = 1.f;
+        if constexpr (GRAD) {
+            float m = 0.f;
+            for (int z = 0; z < 32; ++z) m = fmaxf(m, fabsf(__ldg(p.hdiag + z)));
+            hmax = m > 0.f ? m : 1.f;
+        }
+        const int64_t gwarp = (int64_t)blockIdx.x * G::COMPUTE_WARPS + warp;
+        float* mrow = GRAD ? p.mpart + gwarp * p.rowlen : nullptr;
+        float* frow = GRAD ? mrow + (int64_t)p.S * 16 : nullptr;
+        float* srow = GRAD ? frow + (int64_t)p.K * 16 : nullptr;
+
+        for (int64_t round = 0; round < rounds; ++round) {
+            const int64_t tile = (round * gridDim.x + blockIdx.x) * NT + t;
+            const int64_t b = tile * 128 + quarter * 32 + lane;
+            const bool valid = b < p.B;
+            const int64_t bc = valid ? b : p.B - 1;
+            const float* xrow = ENC == 0 ? p.x + bc * p.ldx : nullptr;
+            const float* u0row = ENC != 0 && p.u0 ? p.u0 + bc * p.ldu0 : nullptr;
+            const float* u1row = ENC != 0 ? p.u1 + bc * p.ldu1 : nullptr;
+            auto load_angles = [&](int k, float(&th)[NQ]) {
+                if constexpr (ENC == 0) {
+#pragma unroll
+                    for (int q = 0; q < NQ; ++q) th[q] = __ldg(xrow + (int64_t)k * NQ + q);
+                } else {
+                    const float* ur = k < p.K0 ? u0row : u1row;
+#pragma unroll
+                    for (int q = 0; q < NQ; ++q) {
+                        const int col = k * NQ + q;
+                        const float u = __ldg(ur + __ldg(p.uidx + col));
+                        th[q] = fmaf(u, __ldg(p.fw + col), p.fb ? __ldg(p.fb + col) : 0.f);
+                    }
+                }
+            };
+            const bool dump = DBG && dbg && blockIdx.x == 0 && t == 0 && round == 0;
+            const int drow = quarter * 32 + lane;
+
+            // ---------------------------------------------------------------- forward sweep
+            float th[NQ];
+            load_angles(0, th);
+            for (int k = 0; k < p.K; ++k) {
+                float thn[NQ];
+                load_angles(k + 1 < p.K ? k + 1 : k, thn);
+                float pr[16], pi[16];
+                tc_phase_table(th, 1.f, pr, pi);
+                if (k > 0) wait_d();
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    uint32_t r[16];
+                    if (k > 0) {
+                        tc::tmem_ld16(tDp + 16u * c, r);
+                        tc::tmem_wait_ld();
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            r[2 * i] = __float_as_uint(kTcSA * 0.17677669529663688110f);
+                            r[2 * i + 1] = 0u;
+                        }
+                    }
+                    if (DBG && dump && k > 0)
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) dbg[((size_t)(k - 1) * 128 + drow) * 128 + 16 * c + i] = __uint_as_float(r[i]);
+                    uint32_t ahi[8], alo[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int z = 8 * c + i;
+                        const u64 v = pack2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
+                        u64 nv;
+                        if (z < 16) {
+                            nv = mul2<0>(pr[z], v);
+                            nv = fma2<2>(pi[z], v, nv);
+                        } else {
+                            nv = mul2<0>(pr[31 - z], v);
+                            nv = fma2<3>(pi[31 - z], v, nv);
+                        }
+                        float xr, xi;
+                        unpack2(nv, xr, xi);
+                        const float hr = __uint_as_float(__float_as_uint(xr) & 0xFFFFE000u);
+                        const float hi_ = __uint_as_float(__float_as_uint(xi) & 0xFFFFE000u);
+                        ahi[i] = tc::cvt_f16x2(hr, hi_);
+                        alo[i] = tc::cvt_f16x2(xr - hr, xi - hi_);
+                    }
+                    tc::tmem_st8(tAp + 8u * c, ahi);
+                    tc::tmem_st8(tAp + 32u + 8u * c, alo);
+                }
+                signal_a();
+#pragma unroll
+                for (int q = 0; q < NQ; ++q) th[q] = thn[q];
+            }
+            wait_d();
+
+            if constexpr (!GRAD) {
+                // ------------------------------------------------------------ expectation value only
+                float e = 0.f, nrm = 0.f;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    uint32_t r[16];
+                    tc::tmem_ld16(tDp + 16u * c, r);
+                    tc::tmem_wait_ld();
+                    if (DBG && dump)
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) dbg[((size_t)(p.K - 1) * 128 + drow) * 128 + 16 * c + i] = __uint_as_float(r[i]);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float re = __uint_as_float(r[2 * i]), im = __uint_as_float(r[2 * i + 1]);
+                        const float pz = fmaf(re, re, im * im);
+                        e = fmaf(__ldg(p.hdiag + 8 * c + i), pz, e);
+                        nrm += pz;
+                    }
+                }
+                // unit norm is exact for the true state; dividing by the computed norm removes the coherent shrink of
+                // the truncating tensor-core accumulation (-4.8e-7 +- 0.7e-7 per GEMM, measured) and the operand scale
+                float res = e / nrm;
+                if (__ldcg(err) != 0) res = __int_as_float(0x7fc00000);
+                if (valid && p.out) p.out[b] = res;
+            } else {
+                // ------------------------------------------------------------ expectation, lam = g H psi
+                uint32_t ps[64], lm[64];
+                tc_load_state(tDp, ps);
+                if (DBG && dump)
+#pragma unroll
+                    for (int i = 0; i < 64; ++i) dbg[((size_t)(p.K - 1) * 128 + drow) * 128 + i] = __uint_as_float(ps[i]);
+                float e = 0.f, nrm = 0.f;
+#pragma unroll
+                for (int z = 0; z < 32; ++z) {
+                    const float re = __uint_as_float(ps[2 * z]), im = __uint_as_float(ps[2 * z + 1]);
+                    const float pz = fmaf(re, re, im * im);
+                    e = fmaf(__ldg(p.hdiag + z), pz, e);
+                    nrm += pz;
+                }
+                e = e / nrm;
+                if (__ldcg(err) != 0) e = __int_as_float(0x7fc00000);
+                if (valid && p.out) p.out[b] = e;
+                float g = 0.f;
+                if (p.target) {   // fused MSE: g = dL/dout for L = gscale/2 * sum (out + bias - y)^2
+                    float resid = 0.f;
+                    if (valid) {
+                        resid = e + (p.bias ? __ldg(p.bias) : 0.f) - __ldg(p.target + b);
+                        g = p.gscale * resid;
+                        if (p.gbuf) p.gbuf[b] = g;
+                    }
+                    float sg = g, sq = resid * resid;
+#pragma unroll
+                    for (int m = 16; m >= 1; m >>= 1) { sg += shfl_xor_(sg, m); sq += shfl_xor_(sq, m); }
+                    if (lane == 0) { atomicAdd(srow, sg); atomicAdd(srow + 1, sq); }
+                } else if (valid) {
+                    g = __ldg(p.gout + b);
+                }
+                // psi to norm sA; lam_hat = (h / hmax) psi (norm <= sA); the scalar g * hmax / sA^2 goes onto the moments
+                const float rn = kTcSA * rsqrtf(nrm);
+                const float glam = g * hmax * (1.f / (kTcSA * kTcSA));
+                const float ihm = 1.f / hmax;
+#pragma unroll
+                for (int z = 0; z < 32; ++z) {
+                    const float re = __uint_as_float(ps[2 * z]) * rn, im = __uint_as_float(ps[2 * z + 1]) * rn;
+                    const float hz = __ldg(p.hdiag + z) * ihm;
+                    ps[2 * z] = __float_as_uint(re);
+                    ps[2 * z + 1] = __float_as_uint(im);
+                    lm[2 * z] = __float_as_uint(re * hz);
+                    lm[2 * z + 1] = __float_as_uint(im * hz);
+                }
+
+                // ------------------------------------------------------------ reverse (adjoint) sweep
+                float* gxrow = NEED_GX ? p.gx + (valid ? b : 0) * p.ldgx : nullptr;
+                int s = p.S;
+                int step = p.K;
+                load_angles(p.K - 1, th);
+                for (int k = p.K - 1; k >= 0; --k) {
+                    float thn[NQ];
+                    load_angles(k > 0 ? k - 1 : 0, thn);
+                    const int d = __ldg(p.depth + k);
+                    for (int j = d - 1; j >= 0; --j, ++step) {
+                        --s;
+                        // Pauli moments of sublayer s on the cut held in registers, scaled by this sample's g
+                        float mv[16];
+                        if (j == d - 1 && k < p.K - 1) tc_moments<true>(ps, lm, mv);
+                        else tc_moments<false>(ps, lm, mv);
+#pragma unroll
+                        for (int i = 0; i < 15; ++i) mv[i] *= glam;
+                        const float tot = butterfly_reduce<float, 16>(mv, lane);
+                        if ((lane & 1) == 0) atomicAdd(mrow + (int64_t)s * 16 + (lane >> 1), tot);
+                        // un-apply the sublayer on both states
+                        tc_store_operand(tAp, ps);
+                        tc_store_operand(tAl, lm);
+                        signal_a();
+                        float pr[16], pi[16];
+                        if (j == 0) tc_phase_table(th, 1.f, pr, pi);
+                        wait_d();
+                        tc_load_state(tDp, ps);
+                        tc_load_state(tDl, lm);
+                        if (DBG && dump) {
+#pragma unroll
+                            for (int i = 0; i < 64; ++i) {
+                                dbg[((size_t)step * 128 + drow) * 128 + i] = __uint_as_float(ps[i]);
+                                dbg[((size_t)step * 128 + drow) * 128 + 64 + i] = __uint_as_float(lm[i]);
+                            }
+                        }
+                        if (j == 0) {
+                            // Hadamard basis, right after the block's encoding layer
+                            if constexpr (WANT_GX) {
+                                float gq[5];
+                                tc_xgrad(ps, lm, gq);
+                                float fv[FREQ_GRAD ? 16 : 1];
+                                if constexpr (FREQ_GRAD) {
+#pragma unroll
+                                    for (int i = 0; i < 16; ++i) fv[i] = 0.f;
+                                }
+#pragma unroll
+                                for (int q = 0; q < NQ; ++q) {
+                                    const float gxv = gq[q] * glam;
+                                    if constexpr (NEED_GX) {
+                                        if (valid) gxrow[(int64_t)k * NQ + q] = gxv;
+                                    }
+                                    if constexpr (FREQ_GRAD) {
+                                        const int col = k * NQ + q;
+                                        const float uval = __ldg((k < p.K0 ? u0row : u1row) + __ldg(p.uidx + col));
+                                        fv[2 * q] = gxv * uval;
+                                        fv[2 * q + 1] = gxv;
+                                    }
+                                }
+                                if constexpr (FREQ_GRAD) {
+                                    const float ft = butterfly_reduce<float, 16>(fv, lane);
+                                    if ((lane & 1) == 0) atomicAdd(frow + (int64_t)k * 16 + (lane >> 1), ft);
+                                }
+                            }
+                            if (s > 0) {
+                                // conjugate phases; the scale restores |psi| = sA (the truncating accumulation shrinks
+                                // both states by the same factor per GEMM), applied to lam as well
+                                float nr = 0.f;
+#pragma unroll
+                                for (int z = 0; z < 32; ++z) {
+                                    const float re = __uint_as_float(ps[2 * z]), im = __uint_as_float(ps[2 * z + 1]);
+                                    nr += fmaf(re, re, im * im);
+                                }
+                                const float corr = kTcSA * rsqrtf(nr);
+#pragma unroll
+                                for (int i = 0; i < 16; ++i) { pr[i] *= corr; pi[i] *= corr; }
+                                tc_apply_phases<true>(ps, pr, pi);
+                                tc_apply_phases<true>(lm, pr, pi);
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int q = 0; q < NQ; ++q) th[q] = thn[q];
+                }
+            }
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == G::COMPUTE_WARPS) tc::tmem_dealloc512(tmem_base);
+}
+
+}  // namespace qon

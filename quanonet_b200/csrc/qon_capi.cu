@@ -534,6 +534,13 @@ int make_plan(int64_t B, int n, int K, const int* depth, int dtype, int mode, Pl
         pl->vp = (3 * n + 3) / 4 * 4;
         pl->fvp = 0;
     }
+    if (dtype == QON_F32 && n == 5) {
+        // the tensor-core tier (hea_tc2.cuh) writes one partial row per compute warp: 8 warps x min(SMs, ceil(B / 256)) CTAs
+        int64_t tcg = (B + 255) / 256;
+        if (tcg > di.sms) tcg = di.sms;
+        if (tcg < 1) tcg = 1;
+        if (pl->rows < (int)tcg * 8) pl->rows = (int)tcg * 8;
+    }
     size_t off = 0;
     pl->off_u = off; off = align_up(off + (size_t)S * n * 4 * es);
     pl->off_r = off; off = align_up(off + (size_t)S * n * 4 * es);
@@ -548,7 +555,7 @@ int make_plan(int64_t B, int n, int K, const int* depth, int dtype, int mode, Pl
     if (pl->fast_hbm) off = align_up(off + pl->hp.bytes);
     else if (pl->tier == 2) off = align_up(off + (size_t)pl->grid * (grad ? 4 : 2) * ((size_t)1 << n) * es);
     pl->off_tc = off;
-    if (dtype == QON_F32 && n == 5) off = align_up(off + tc_workspace_bytes(K));   // tensor-core tier: block matrices
+    if (dtype == QON_F32 && n == 5) off = align_up(off + tc_workspace_bytes(K, (int)S));   // tensor-core tier: operand images
     pl->total = off;
     return 0;
 }
@@ -648,13 +655,13 @@ int run(const Job& j) {
         const TcConfig& tcc = tc_config();
         bool use_tc = false;
         if constexpr (sizeof(T) == 4)
-            use_tc = tcc.enable && n == 5 && (mode == 0 || mode == 3) && j.ham_kind == QON_HAM_DIAG && j.B >= tcc.min_batch;
+            use_tc = tcc.enable && n == 5 && j.ham_kind == QON_HAM_DIAG && j.B >= tcc.min_batch;
         if (use_tc) {
             if constexpr (sizeof(T) == 4) {
                 int dev; DeviceInfo di;
                 if (!device_info(&dev, &di)) return fail(QON_ERR_NO_DEVICE, "no usable CUDA device");
-                e = tc_forward_launch(mode, di.sms, (const HeaParams<float>&)p, (const float*)j.w, dp, base + pl.off_tc,
-                                      tcc.dbg, tcc.err, st);
+                e = tc_launch(mode, tcc.enable == 2 ? 1 : 2, di.sms, (const HeaParams<float>&)p, (const float*)j.w, dp,
+                              base + pl.off_tc, tcc.dbg, tcc.err, st);
             } else e = cudaErrorInvalidValue;
         } else if (pl.fast_warp) {
             if constexpr (sizeof(T) == 4) e = warp_launch_f32(n, mode, pl.grid, pl.wp, (const HeaParams<float>&)p, dp, st);

@@ -76,9 +76,37 @@ def test_parse_experiment_dir():
     assert cfg["net_size"] == (40, 2, 20, 2) and cfg["num_qubits"] == 5 and cfg["if_trainable_freq"]
     assert cfg["scale_coeff"] == 0.1 and cfg["num_points"] == 25 and cfg["operator"] == "Darcy"
     cfg = ck.parse_experiment_dir("x/Antideriv_HEAQNN_Net32-2_Q3_S0.01_100x10_Seed3")
-    assert cfg["model_type"] == "HEAQNN" and not cfg["if_trainable_freq"] and cfg["net_size"] == (32, 2)
+    assert cfg["model_type"] == "HEAQNN" and "if_trainable_freq" not in cfg and cfg["net_size"] == (32, 2)
     with pytest.raises(ValueError):
         ck.parse_experiment_dir("nothing/here")
+
+
+def test_parse_experiment_dir_reference_naming_scheme():
+    """Every suffix the reference's utils/logger.py:55-118 can write: _TF/_FF, _Pauli*, _Diag*/_Ham*, the backend tag."""
+    P = ck.parse_experiment_dir
+    cfg = P("outputs/Advection/Advection_QuanONet_Net40-2-20-2_Q5_TF_S0.1_TQ_1000x100_Seed0/best_model.pt")
+    assert cfg["quantum_backend"] == "torchquantum" and cfg["if_trainable_freq"] is True
+    assert (cfg["num_train"], cfg["num_points"], cfg["seed"]) == (1000, 100, 0) and cfg["scale_coeff"] == 0.1
+    cfg = P("Antideriv_QuanONet_Net5-1-5-1_Q2_FF_S0.001_1000x100_Seed0")
+    assert cfg["if_trainable_freq"] is False and cfg["net_size"] == (5, 1, 5, 1) and cfg["scale_coeff"] == 0.001
+    cfg = P("RDiffusion_HEAQNN_Net64-2_Q5_TF_S0.01_PauliX_1000x100_Seed3")
+    assert cfg["ham_pauli"] == "X" and cfg["model_type"] == "HEAQNN" and cfg["net_size"] == (64, 2) and cfg["seed"] == 3
+    cfg = P("Darcy_QuanONet_Net20-2-10-2_Q5_TF_S0.01_Ham-1-1_1000x25_Seed0")
+    assert cfg["ham_bound"] == (-1.0, 1.0) and cfg["num_points"] == 25 and "ham_pauli" not in cfg
+    cfg = P("Darcy_QuanONet_Net20-2-10-2_Q5_TF_S0.01_PauliY_Ham-10-10_Qiskit_1000x25_Seed0")
+    assert cfg["ham_bound"] == (-10.0, 10.0) and cfg["ham_pauli"] == "Y" and cfg["quantum_backend"] == "qiskit"
+    cfg = P("Antideriv_QuanONet_Net50-2-50-2_Q2_TF_S0.01_Diag-5--2.5-2.5-5_PL_1000x100_Seed1")
+    assert cfg["ham_diag"] == [-5.0, -2.5, 2.5, 5.0] and cfg["quantum_backend"] == "pennylane"
+    cfg = P("Antideriv_QuanONet_Net50-2-50-2_Q2_TF_S0.01_Diag-5-5-5-5_1000x100_Seed1")
+    assert cfg["ham_diag"] == [-5.0, 5.0, 5.0, 5.0]
+
+
+def test_infer_config_from_reference_style_names():
+    from quanonet_b200.infer import _resolve_config
+    cfg = _resolve_config("o/Advection_QuanONet_Net40-2-20-2_Q5_FF_S0.1_TQ_1000x100_Seed0/best_model.pt", {})
+    assert cfg["model_type"] == "QuanONet" and cfg["if_trainable_freq"] is False
+    cfg = _resolve_config("o/RDiffusion_HEAQNN_Net64-2_Q5_TF_S0.01_PauliX_Ham-1-1_1000x100_Seed3/final_model.npz", {})
+    assert cfg["ham_pauli"] == "X" and tuple(cfg["ham_bound"]) == (-1.0, 1.0) and cfg["if_trainable_freq"] is True
 
 
 def test_shipped_checkpoint_fixture_values():
