@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define QON_ABI_VERSION 2   /* 2: + qon_latency_tier_max_batch, qon_peer_*, qon_encoded_mse_step_dp */
+#define QON_ABI_VERSION 3   /* 2: + qon_latency_tier_max_batch, qon_peer_*, qon_encoded_mse_step_dp; 3: + qon_tensor_tier */
 
 /* dtype: arithmetic type of x, w, out, gradients and the state */
 #define QON_F32 0 /* float32 / complex64  — parity with the TorchQuantum path            */
@@ -152,6 +152,10 @@ int64_t qon_latency_tier_max_batch(void);
  * B samples at n qubits in `dtype` on the current device, else 0: n <= 5 (fp32) / n <= 4 (fp64) at any batch size,
  * and n = 6..9 in fp32 for batches small enough for the wide latency tier. */
 int qon_encoded_supported(int64_t B, int n, int dtype, int need_grad);
+/* The same question for a concrete circuit (K blocks, depth_per_block): for n = 6..9 the answer depends on the
+ * circuit's size (the wide latency tier stages the whole gate table and the sample's angles in shared memory), so
+ * callers that know the circuit ask this one and fall back to the x-given entry points on 0. */
+int qon_encoded_supported_for(int64_t B, int n, int K, const int* depth_per_block, int dtype, int need_grad);
 
 /* Exchange step of the data-parallel training step (the reference has no multi-GPU path — main.py:52
  * pins one GPU — so this replaces the torch.distributed all_reduce a DDP port would add at
@@ -179,6 +183,18 @@ int qon_encoded_mse_step_dp(const void* u0, int64_t ldu0, int in0, int K0, const
                             int64_t max_len, int64_t B, int n, int K, const int* depth_per_block, const void* ham_diag,
                             int diag_order, double ham_offset, double ham_coeff, int ham_kind, void* workspace,
                             size_t workspace_bytes, void* stream);
+
+/* Tensor-core tier (n = 5, fp32, diagonal observable — csrc/hea_tc.cuh, hea_tc2.cuh): every entry point above
+ * routes batches of at least `min_batch` samples to it: the ansatz sublayers of a block (sample-independent in the
+ * reference, core/quantum_circuits_tq.py:89-101) pre-fused into one 32x32 unitary and applied as split-f16 GEMMs on
+ * tcgen05 tensor cores, the RX encoding layers as diagonal phases in the Hadamard basis; same results to the 1e-5
+ * norm-relative bar.  On by default (QON_TC=0 in the environment disables it; QON_TC_MIN_B sets the threshold).
+ *   enable     1 = on, 0 = off (the FFMA2 register kernels serve every batch), -1 = leave unchanged
+ *   min_batch  smallest batch routed to the tier (default 16384); < 0 = leave unchanged
+ *   debug_state / error_flag: device pointers for kernel bring-up (state dump of the first tile; protocol
+ *   time-out flag), NULL in production — a time-out poisons the outputs with NaN, it never hangs.
+ * Process-wide; returns the previous `enable`. */
+int qon_tensor_tier(int enable, int64_t min_batch, void* debug_state, void* error_flag);
 
 /* FP32 FFMA-saturating micro-benchmark (the metric is "% of FP32 peak" and MEASURED_PEAKS.json has
  * no FP32 entry): runs `iters` dependent-chain FFMA rounds on every SM and returns achieved

@@ -16,7 +16,7 @@ LIB_PATH = os.environ.get("QON_LIB_PATH") or os.path.join(PKG_DIR, "libquanonet_
 QON_F32, QON_F64 = 0, 1
 QON_HAM_DIAG, QON_HAM_PAULI_X, QON_HAM_PAULI_Y = 0, 1, 2
 QON_DIAG_LSB0, QON_DIAG_MSB0 = 0, 1
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 # every symbol include/quanonet_b200.h declares
 EXPORTED_SYMBOLS = (
@@ -31,10 +31,12 @@ EXPORTED_SYMBOLS = (
     "qon_plan_tier",
     "qon_latency_tier_max_batch",
     "qon_encoded_supported",
+    "qon_encoded_supported_for",
     "qon_peer_buffer_bytes",
     "qon_peer_allreduce_f32",
     "qon_encoded_mse_step_dp",
     "qon_measure_fp32_peak_tflops",
+    "qon_tensor_tier",
 )
 
 _lock = threading.Lock()
@@ -71,6 +73,8 @@ def _declare(lib):
     lib.qon_encoded_mse_step.argtypes = enc_head + [vp, vp, vp, dbl, vp, vp, vp, vp, vp, i64, i32, i32, ip] + ham_tail
     lib.qon_encoded_supported.restype = i32
     lib.qon_encoded_supported.argtypes = [i64, i32, i32, i32]
+    lib.qon_encoded_supported_for.restype = i32
+    lib.qon_encoded_supported_for.argtypes = [i64, i32, i32, ip, i32, i32]
     lib.qon_latency_tier_max_batch.restype = i64
     lib.qon_latency_tier_max_batch.argtypes = []
     lib.qon_peer_buffer_bytes.restype = sz
@@ -83,6 +87,8 @@ def _declare(lib):
                                             i64, i32, i32, ip, vp, i32, dbl, dbl, i32, vp, sz, vp]
     lib.qon_plan_tier.restype = i32
     lib.qon_plan_tier.argtypes = [i64, i32, i32, i32, ip]
+    lib.qon_tensor_tier.restype = i32
+    lib.qon_tensor_tier.argtypes = [i32, i64, vp, vp]
     lib.qon_measure_fp32_peak_tflops.restype = dbl
     lib.qon_measure_fp32_peak_tflops.argtypes = [i32, vp]
 

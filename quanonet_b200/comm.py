@@ -21,25 +21,38 @@ from . import _lib
 class PeerAllReduce:
     """In-place sum all-reduce of a contiguous fp32 CUDA tensor with at most ``max_len`` elements."""
 
-    def __init__(self, max_len: int, device: torch.device, group=None):
+    def __init__(self, max_len: int, device: torch.device, group=None, connect: bool = True):
+        """Construction has a LOCAL half (allocation, capability checks — may raise on one rank only) and a
+        COLLECTIVE half (``connect``: handle exchange + barrier).  ``make_all_reduce`` runs the local half on every
+        rank, agrees on the outcome with an all-reduce(MIN), and only then enters the collective half — so a rank
+        whose allocation fails never leaves its peers blocked in a rendezvous."""
         import torch.distributed._symmetric_memory as symm_mem
 
         self.group = group if group is not None else dist.group.WORLD
         self.world = dist.get_world_size(self.group)
         self.rank = dist.get_rank(self.group)
         self.max_len = int(max_len)
+        self.device = device
         self.lib = _lib.load()
         nbytes = int(self.lib.qon_peer_buffer_bytes(self.max_len, self.world))
         if nbytes == 0:
             raise RuntimeError(f"peer all-reduce supports world <= 8 (got {self.world})")
         self.buf = symm_mem.empty(nbytes, dtype=torch.uint8, device=device)
         self.buf.zero_()
+        self.ptrs = None
+        if connect:
+            self.connect()
+
+    def connect(self):
+        """Collective: every rank of the group must call it."""
+        import torch.distributed._symmetric_memory as symm_mem
+
         self.handle = symm_mem.rendezvous(self.buf, self.group)
         ptrs = [int(p) for p in self.handle.buffer_ptrs]
         if len(ptrs) != self.world or ptrs[self.rank] != self.buf.data_ptr():
             raise RuntimeError("symmetric-memory rendezvous returned unexpected peer pointers")
         self.ptrs = (ctypes.c_void_p * self.world)(*ptrs)
-        torch.cuda.synchronize(device)
+        torch.cuda.synchronize(self.device)
         dist.barrier(self.group)          # every rank's buffer is zeroed before anyone pushes
 
     def __call__(self, flat: torch.Tensor) -> torch.Tensor:
@@ -72,13 +85,14 @@ def make_all_reduce(flat: torch.Tensor, group=None) -> Callable[[torch.Tensor], 
         return nccl
     peer, err = None, None
     try:
-        peer = PeerAllReduce(flat.numel(), flat.device, group)
+        peer = PeerAllReduce(flat.numel(), flat.device, group, connect=False)     # local half only
     except Exception as exc:    # symmetric memory unavailable (no P2P, older driver ...)
         err = exc
-    # every rank must take the same path: agree on the outcome before anyone uses it
+    # every rank must take the same path: agree on the outcome BEFORE the collective half of the construction
     ok = torch.tensor([1 if peer is not None else 0], device=flat.device, dtype=torch.int32)
     dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
     if int(ok.item()) == 1:
+        peer.connect()
         return peer
     if choice == "peer":
         raise RuntimeError(f"peer-memory all-reduce unavailable on at least one rank ({err})")

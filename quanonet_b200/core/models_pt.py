@@ -73,8 +73,10 @@ def _can_fuse_inference(qlayer, u):
         return False
     from ..ops import encoded_supported
     w = qlayer.ansatz_weights
-    return (encoded_supported(qlayer.n_wires, w.dtype, int(u.shape[0]), need_grad=False)
-            and all(e == qlayer.n_wires and d >= 1 for e, d in qlayer.block_configs))
+    if not all(e == qlayer.n_wires and d >= 1 for e, d in qlayer.block_configs):
+        return False
+    return encoded_supported(qlayer.n_wires, w.dtype, int(u.shape[0]), need_grad=False,
+                             depths=[d for _, d in qlayer.block_configs])
 
 
 def _fused_inference(qlayer, layers, u0, u1, enc0):

@@ -30,13 +30,14 @@ int fail(int code, const char* fmt, ...) {
 
 constexpr int kMaxQubits = 24;
 
-// Tensor-core tier switch (hea_tc.cuh): QON_TC=0/1 in the environment, or qon_tc_config() at run time.
+// Tensor-core tier switch (hea_tc.cuh, hea_tc2.cuh): QON_TC=0/1 in the environment, or qon_tensor_tier() at run time
+// (enable == 2 selects the first forward-only kernel of hea_tc.cuh, kept for A/B runs).
 struct TcConfig { int enable; float* dbg; int* err; int64_t min_batch; };
 TcConfig& tc_config() {
     static TcConfig c = [] {
         const char* e = getenv("QON_TC");
         const char* m = getenv("QON_TC_MIN_B");
-        return TcConfig{e ? atoi(e) : 0, nullptr, nullptr, m ? (int64_t)atoll(m) : (int64_t)16384};
+        return TcConfig{e ? atoi(e) : 1, nullptr, nullptr, m ? (int64_t)atoll(m) : (int64_t)16384};
     }();
     return c;
 }
@@ -765,6 +766,15 @@ int qon_encoded_supported(int64_t B, int n, int dtype, int need_grad) {
     return rc == 0 ? 1 : 0;
 }
 
+int qon_encoded_supported_for(int64_t B, int n, int K, const int* depth_per_block, int dtype, int need_grad) {
+    // planned with the REAL circuit: the wide latency tier's shared-memory footprint grows with K and S, so a
+    // deep n = 6..9 circuit can fit the one-block probe of qon_encoded_supported() and still have no kernel
+    if (K < 1 || !depth_per_block) return 0;
+    Plan pl;
+    const int rc = make_plan(B, n, K, depth_per_block, dtype, need_grad ? 5 : 3, &pl);
+    return rc == 0 ? 1 : 0;
+}
+
 size_t qon_peer_buffer_bytes(int64_t max_len, int world) {
     if (max_len < 1 || world < 1 || world > kPeerMaxWorld) return 0;
     return peer_buffer_bytes(max_len, world);
@@ -902,12 +912,14 @@ int qon_encoded_mse_step_dp(const void* u0, int64_t ldu0, int in0, int K0, const
     return dispatch(j);
 }
 
-void qon_tc_config(int enable, void* dbg, void* err, int64_t min_batch) {
+int qon_tensor_tier(int enable, int64_t min_batch, void* debug_state, void* error_flag) {
     TcConfig& c = tc_config();
-    c.enable = enable;
-    c.dbg = (float*)dbg;
-    c.err = (int*)err;
+    const int prev = c.enable;
+    if (enable >= 0) c.enable = enable;
     if (min_batch >= 0) c.min_batch = min_batch;
+    c.dbg = (float*)debug_state;
+    c.err = (int*)error_flag;
+    return prev;
 }
 
 double qon_measure_fp32_peak_tflops(int iters, void* stream) {

@@ -195,6 +195,17 @@ def fp32_peak_tflops(iters: int = 2000) -> float:
     return float(v)
 
 
+def tensor_tier(enable: Optional[bool] = None, min_batch: Optional[int] = None, debug_state=None, error_flag=None) -> bool:
+    """Switch / query the tensor-core tier (``qon_tensor_tier``): n = 5, fp32, diagonal observables, batches of at
+    least ``min_batch`` samples.  Returns the previous setting.  ``debug_state`` / ``error_flag`` are device tensors
+    used by the bring-up scripts only."""
+    prev = _lib.load().qon_tensor_tier(-1 if enable is None else int(bool(enable)) if not isinstance(enable, int) else int(enable),
+                                       -1 if min_batch is None else int(min_batch),
+                                       None if debug_state is None else debug_state.data_ptr(),
+                                       None if error_flag is None else error_flag.data_ptr())
+    return bool(prev)
+
+
 def latency_tier_max_batch() -> int:
     """Largest per-call batch served by the small-batch latency tier (n <= 5, angles given)."""
     return int(_lib.load().qon_latency_tier_max_batch())
@@ -409,12 +420,18 @@ def _(u0, u1, fw, fb, K0, weights, target, bias, grad_scale, n_wires, depth_per_
     return torch.empty_like(weights), g, u1.new_empty(g.shape), u1.new_empty((2,))
 
 
-def encoded_supported(n_wires: int, dtype=torch.float32, batch: Optional[int] = None, need_grad: bool = True) -> bool:
+def encoded_supported(n_wires: int, dtype=torch.float32, batch: Optional[int] = None, need_grad: bool = True,
+                      depths: Optional[List[int]] = None) -> bool:
     """Whether the fused-encoding kernels serve this problem: always for n <= 5 (fp32) / n <= 4 (fp64); for
-    n = 6..9 in fp32 only when ``batch`` is given and small enough for the wide latency tier
-    (``qon_encoded_supported`` asks the planner)."""
+    n = 6..9 in fp32 only when ``batch`` is given and small enough for the wide latency tier — and, because that
+    tier's shared-memory footprint grows with the circuit, only if the planner accepts the real circuit
+    (``depths``; ``qon_encoded_supported_for``).  Without ``depths`` a one-block probe is planned."""
     if n_wires <= (5 if dtype == torch.float32 else 4):
         return True
     if batch is None or dtype != torch.float32 or not 6 <= n_wires <= 9:
         return False
-    return bool(_lib.load().qon_encoded_supported(int(batch), int(n_wires), _DTYPES[dtype], int(need_grad)))
+    lib = _lib.load()
+    if depths:
+        return bool(lib.qon_encoded_supported_for(int(batch), int(n_wires), len(depths), _lib.int_array(depths),
+                                                  _DTYPES[dtype], int(need_grad)))
+    return bool(lib.qon_encoded_supported(int(batch), int(n_wires), _DTYPES[dtype], int(need_grad)))

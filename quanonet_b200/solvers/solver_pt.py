@@ -98,9 +98,10 @@ class B200Solver:
         epochs = int(self.config["num_epochs"])
         num_batches = max(1, int(np.ceil(n / bs)))
         out_dir = self.config.get("output_dir")
-        if out_dir and self.rank == 0:
-            os.makedirs(out_dir, exist_ok=True)
-            self.best_model_path = os.path.join(out_dir, "best_model.pt")
+        if out_dir:
+            if self.rank == 0:
+                os.makedirs(out_dir, exist_ok=True)
+            self.best_model_path = os.path.join(out_dir, "best_model.pt")     # every rank knows it; rank 0 writes it
         history = {"loss_train": [], "loss_test": [], "rel_l2_train": []}
         gen = torch.Generator(device=self.device)
         gen.manual_seed(int(self.config.get("seed", 0)))       # same permutation on every rank
@@ -162,8 +163,7 @@ class B200Solver:
                 loss_sum += loss
                 sse += loss * gb
             avg = float(loss_sum) / num_batches                   # one host sync per epoch
-            ar = getattr(self.trainer, "_all_reduce", None)
-            if hasattr(ar, "timed_out") and ar.timed_out():
+            if self.trainer.exchange_timed_out():
                 raise RuntimeError("the peer-memory all-reduce gave up waiting for a rank (~30 s); gradients of that "
                                    "step were NaN-poisoned — check that every rank is alive, or set QON_COLLECTIVE=nccl")
             rel = float(torch.sqrt(sse) / (torch.linalg.norm(self.train_out) + 1e-8))
@@ -177,10 +177,22 @@ class B200Solver:
                     np.savez(self.best_model_path.replace(".pt", ".npz"), **{k: v.cpu().numpy() for k, v in sd.items()})
             if self.scheduler is not None:
                 self.scheduler.step()
+        # final checkpoint, as the reference writes it (solvers/solver_pt.py:262-270)
+        if out_dir and self.rank == 0 and self.config.get("if_save", True):
+            sd = self.model.state_dict()
+            final = os.path.join(out_dir, "final_model.pt")
+            torch.save(sd, final)
+            np.savez(final.replace(".pt", ".npz"), **{k: v.cpu().numpy() for k, v in sd.items()})
         return history
 
     @torch.no_grad()
     def evaluate(self):
+        # EVERY rank reloads the best weights (rank 0 wrote them): replicas stay identical, so metrics agree across
+        # ranks and a later train() call is still data-parallel on identical replicas
+        if self.world > 1:
+            if self.device.type == "cuda":
+                torch.cuda.synchronize(self.device)
+            dist.barrier()
         if self.best_model_path and os.path.exists(self.best_model_path):
             self.model.load_state_dict(torch.load(self.best_model_path, map_location=self.device))
         self.model.eval()

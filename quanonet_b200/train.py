@@ -151,7 +151,8 @@ class DataParallelTrainer:
             fused = self._enc_by_batch.get(B)
             if fused is None:
                 from .ops import encoded_supported
-                fused = self._enc_by_batch[B] = encoded_supported(q.n_wires, q.ansatz_weights.dtype, B)
+                fused = self._enc_by_batch[B] = encoded_supported(q.n_wires, q.ansatz_weights.dtype, B,
+                                                                  depths=[d for _, d in q.block_configs])
         if fused:
             return self._compute_grads_fused(inputs, y, scale, gB)
         if self.is_onet:
@@ -264,6 +265,13 @@ class DataParallelTrainer:
         loss = self.compute_grads(inputs, y, global_batch)
         self.optimizer.step()
         return loss
+
+    def exchange_timed_out(self) -> bool:
+        """True if the peer-memory exchange ever gave up waiting for a rank (~30 s): the gradients of that step were
+        NaN-poisoned on purpose, so the loss and the parameters are NaN from then on.  One host sync — poll it per
+        epoch (``B200Solver`` does), not per step."""
+        ar = self._all_reduce
+        return bool(hasattr(ar, "timed_out") and ar.timed_out())
 
 
 def autograd_step(model, optimizer, inputs, y, loss_fn=None):

@@ -16,15 +16,13 @@ import tc_emulate as emu
 OUT = os.path.join(ROOT, "gpurun_out")
 os.makedirs(OUT, exist_ok=True)
 lib = _lib.load()
-lib.qon_tc_config.restype = None
-lib.qon_tc_config.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64]
 dev = torch.device("cuda:0")
 n = 5
 results = {}
 
 
 def run(x, w, depths, tc, dbg=None, err=None, min_b=0):
-    lib.qon_tc_config(int(tc), None if dbg is None else dbg.data_ptr(), None if err is None else err.data_ptr(), min_b)
+    lib.qon_tensor_tier(int(tc), min_b, None if dbg is None else dbg.data_ptr(), None if err is None else err.data_ptr())
     out = hea_expval(x, w, n, list(depths), None, 0, 0.0, 1.0, 0)
     torch.cuda.synchronize()
     return out[:, 0].double().cpu().numpy()
@@ -40,7 +38,7 @@ def case(depths, B, seed, dump=False):
     ref = orc.hea_forward(x[:nref], w, n, blocks, orc.ham_from_bound(n))
     xt = torch.tensor(x, dtype=torch.float32, device=dev)
     wt = torch.tensor(w, dtype=torch.float32, device=dev)
-    dbg = torch.zeros(K * 128 * 64, dtype=torch.float32, device=dev) if dump else None
+    dbg = torch.zeros(K * 128 * 128, dtype=torch.float32, device=dev) if dump else None
     err = torch.zeros(1, dtype=torch.int32, device=dev)
     o_tc = run(xt, wt, depths, True, dbg, err)
     o_reg = run(xt, wt, depths, False)
@@ -52,7 +50,7 @@ def case(depths, B, seed, dump=False):
           flush=True)
     results[f"K{K}_S{S}_B{B}"] = dict(tc_vs_oracle=e_tc, ffma2_vs_oracle=e_reg, tc_vs_ffma2=e_x, err=flag)
     if dump:
-        d = dbg.cpu().numpy().reshape(K, 128, 64)
+        d = dbg.cpu().numpy().reshape(K, 128, 128)[:, :, :64]
         # expected scaled state after block k's GEMM, exact arithmetic
         s0 = 0
         exp = np.zeros((K, min(B, 128), 64))
@@ -81,7 +79,7 @@ def bench(B=1_000_000, depths=(2,) * 60, iters=5):
     w = (torch.rand(S, 3, n, generator=g) * 2 - 1).mul_(np.pi).to(dev)
     res = {}
     for name, tc in (("ffma2", False), ("tc", True)):
-        lib.qon_tc_config(int(tc), None, None, 0)
+        lib.qon_tensor_tier(int(tc), 0, None, None)
         for _ in range(2):
             hea_expval(x, w, n, list(depths), None, 0, 0.0, 1.0, 0)
         torch.cuda.synchronize()

@@ -18,8 +18,6 @@ import tc_emulate_bwd as emub
 OUT = os.path.join(ROOT, "gpurun_out")
 os.makedirs(OUT, exist_ok=True)
 lib = _lib.load()
-lib.qon_tc_config.restype = None
-lib.qon_tc_config.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64]
 dev = torch.device("cuda:0")
 n = 5
 results = {}
@@ -27,7 +25,7 @@ rel = lambda a, b: float(np.linalg.norm(np.asarray(a, float) - np.asarray(b, flo
 
 
 def cfg(tc, dbg=None, err=None):
-    lib.qon_tc_config(int(tc), None if dbg is None else dbg.data_ptr(), None if err is None else err.data_ptr(), 0)
+    lib.qon_tensor_tier(int(tc), 0, None if dbg is None else dbg.data_ptr(), None if err is None else err.data_ptr())
 
 
 def case(depths, B, seed, need_gx=True, dump=False):

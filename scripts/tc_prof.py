@@ -6,11 +6,9 @@ sys.path.insert(0, ROOT)
 from quanonet_b200 import _lib
 from quanonet_b200.ops import hea_expval
 lib = _lib.load()
-lib.qon_tc_config.restype = None
-lib.qon_tc_config.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64]
 tc = int(sys.argv[1]) if len(sys.argv) > 1 else 1
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 148 * 512 * 4
-lib.qon_tc_config(tc, None, None, 0)
+lib.qon_tensor_tier(tc, 0, None, None)
 dev = torch.device("cuda:0")
 n, depths = 5, [2] * 60
 g = torch.Generator().manual_seed(0)
