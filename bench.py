@@ -325,6 +325,25 @@ def run_b200(args):
         sync_all()
         trainer._fused_exchange = True
     kern_ms = float(np.mean([a.elapsed_time(b) for a, b in kernel_events]))
+    # the same kernel call on the FFMA2 register kernels (tensor-core tier switched off), for the A/B in the record
+    from quanonet_b200.ops import tensor_tier
+    tc_on = bool(tensor_tier(None)) and B >= 16384 and not args.unfused
+    ffma2_ms = None
+    if tc_on and rank == 0 or (tc_on and world > 1):
+        saved_fx = getattr(trainer, "_fused_exchange", False)
+        trainer._fused_exchange = False
+        tensor_tier(False)
+        kernel_events.clear()
+        saved_ar = trainer._all_reduce
+        trainer._all_reduce = (lambda t: t) if world > 1 else saved_ar      # kernels only; replicas resynchronised below
+        flat_saved = trainer.flat_param.detach().clone()
+        for _ in range(3):
+            trainer.compute_grads((branch, trunk), y)
+        sync_all()
+        ffma2_ms = float(np.mean([a.elapsed_time(b) for a, b in kernel_events][1:]))
+        tensor_tier(True)
+        trainer._all_reduce, trainer._fused_exchange = saved_ar, saved_fx
+        trainer.flat_param.copy_(flat_saved)
     trainer.kernel_events = None
 
     # ---- strong scaling (BASELINE config 3): the SAME global batch of `B` samples sharded B/N per GPU
@@ -465,16 +484,24 @@ def run_b200(args):
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "ms_per_step": e2e_ms / K, "timer": "max(CUDA events, host wall clock) over the K steps, max over ranks"},
             # this library's kernels per step: prep, circuit kernel, finalize (+ finalize_enc) — with N > 1 the
-            # finalize kernel is also the all-reduce (finalize_exchange_kernel), else one peer all-reduce kernel more
-            "gpu_launches": (3 if getattr(trainer, "_fused_exchange", False) else
-                             (4 if trainer.fused_encoding else 3) + (1 if world > 1 else 0)) * K,
+            # finalize kernel is also the all-reduce (finalize_exchange_kernel), else one peer all-reduce kernel more;
+            # the tensor-core tier adds its two operand-image prep kernels
+            "gpu_launches": ((3 if getattr(trainer, "_fused_exchange", False) else
+                              (4 if trainer.fused_encoding else 3) + (1 if world > 1 else 0)) + (2 if tc_on else 0)) * K,
             "roofline": {"bound": "fp32", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                          "frac": achieved / peak if peak else None, "traffic": traffic,
-                         "kernel": "hea_reg_kernel<float,5,0,grad%s> (+prep, finalize)" % (
+                         "kernel": ("hea_tc_kernel<grad%s> (tcgen05 block-unitary GEMMs + FFMA2 phases / Pauli moments; +prep, finalize)"
+                                    if tc_on else "hea_reg_kernel<float,5,0,grad%s> (+prep, finalize)") % (
                              ",fused-encoding" if trainer.fused_encoding else ""), "kernel_ms": kern_ms,
                          "flops_per_sample": f_all, "peak_source": "FFMA probe measured on this GPU in this run "
                          "(MEASURED_PEAKS.json has no FP32 entry)", "peak_nominal": nominal,
-                         "frac_of_nominal": achieved / nominal},
+                         "frac_of_nominal": achieved / nominal,
+                         "note": ("ALGORITHMIC gate-by-gate flops (SURVEY §8d) over the FP32 CUDA-core peak; with the tensor-core "
+                                  "tier on, the sample-independent sublayers run as split-f16 GEMMs on tcgen05 (executed tensor "
+                                  "flops are not credited), so the fraction can approach or exceed 1" if tc_on else
+                                  "ALGORITHMIC gate-by-gate flops (SURVEY §8d) over the FP32 CUDA-core peak")},
+            "tensor_tier": {"enabled": tc_on, "min_batch": 16384,
+                            "ffma2_kernel_ms": ffma2_ms, "ffma2_samples_per_s": (B / (ffma2_ms * 1e-3)) if ffma2_ms else None},
             "per_step": trace,
             "forward_only": {"value": B / (fwd_ms * 1e-3), "unit": "samples/s",
                              "tflops": f_fwd * B / (fwd_ms * 1e-3) / 1e12},

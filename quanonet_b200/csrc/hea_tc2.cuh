@@ -22,14 +22,20 @@
 
 namespace qon {
 
-template <bool GRAD> struct TcGeom {
-    static constexpr int NT = GRAD ? 2 : 4;                 // tiles per CTA
+// SEQ (gradient kernels only): 3 tiles of 128 TMEM columns each (one operand region A, one accumulator D); a reverse
+// step runs its two GEMMs one after the other through them (psi, then lam).  !SEQ: 2 tiles of 256 columns, both GEMMs
+// of a reverse step in flight at once.  More tiles = more warps to hide latencies; registers (psi + lam = 128 per
+// thread) cap the CTA at 12 compute warps.
+template <bool GRAD, bool SEQ = false> struct TcGeom {
+    static constexpr int NT = GRAD ? (SEQ ? 3 : 2) : 4;     // tiles per CTA
     static constexpr int NS = GRAD ? 4 : 3;                 // B-image ring stages per tile
     static constexpr int COMPUTE_WARPS = 4 * NT;
     static constexpr int WARPS = COMPUTE_WARPS + 4;         // + one warpgroup hosting the NT MMA warps
     static constexpr int THREADS = WARPS * 32;
-    static constexpr int TILE_COLS = GRAD ? 256 : 128;      // TMEM columns per tile
+    static constexpr int TILE_COLS = GRAD && !SEQ ? 256 : 128;   // TMEM columns per tile
     static constexpr int SMEM = NT * NS * kTcImgBytes;
+    // register hand-over (setmaxnreg) from the MMA warpgroup to the compute warps; both sum to 64K registers
+    static constexpr int REGS_COMPUTE = SEQ ? 160 : 232, REGS_MMA = SEQ ? 32 : 40;
 };
 
 // a (.) P(z) + c with the operand patterns of ffma2.cuh applied to the packed operand z
@@ -235,10 +241,11 @@ __device__ __forceinline__ bool tc_wait(uint32_t bar, uint32_t parity, int* err)
 // the kernel.  ENC as in hea_reg.cuh (0: x given, 1: fused encoding, 2: + frequency-layer gradients)
 // images: [K forward block images | S reverse sublayer images in sweep order]
 // ---------------------------------------------------------------------------------------------------------
-template <bool GRAD, bool NEED_GX, int ENC, bool DBG>
-__global__ void __launch_bounds__(TcGeom<GRAD>::THREADS, 1)
+template <bool GRAD, bool NEED_GX, int ENC, bool DBG, bool SEQ>
+__global__ void __launch_bounds__(TcGeom<GRAD, SEQ>::THREADS, 1)
 hea_tc_kernel(const HeaParams<float> p, const unsigned char* __restrict__ images, float* dbg, int* err) {
-    using G = TcGeom<GRAD>;
+    using G = TcGeom<GRAD, SEQ>;
+    static_assert(GRAD || !SEQ, "SEQ is a gradient-kernel layout");
     constexpr int NQ = 5, NT = G::NT, NS = G::NS;
     constexpr bool FREQ_GRAD = GRAD && ENC == 2;
     constexpr bool WANT_GX = NEED_GX || FREQ_GRAD;
@@ -268,11 +275,11 @@ hea_tc_kernel(const HeaParams<float> p, const unsigned char* __restrict__ images
 
     if (warp >= G::COMPUTE_WARPS) {
         // =================================================== MMA warps: one elected thread per tile
-        if constexpr (GRAD) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");   // hand registers to the compute warps
+        if constexpr (GRAD) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(G::REGS_MMA));   // hand registers to the compute warps
         const int t = warp - G::COMPUTE_WARPS;
         if (t < NT && lane == 0) {
             const uint32_t mD = tmem_base + (uint32_t)t * G::TILE_COLS;
-            const uint32_t mA = mD + (GRAD ? 128u : 64u);
+            const uint32_t mA = mD + (GRAD && !SEQ ? 128u : 64u);
             const uint32_t ring = tc::smem_u32(tc_smem + (size_t)t * NS * kTcImgBytes);
             const uint32_t bar_a_t = tc::smem_u32(&bar_a[t]), bar_d_t = tc::smem_u32(&bar_d[t]);
             constexpr uint32_t idesc = tc::idesc_f16(128, 64);
@@ -285,29 +292,34 @@ hea_tc_kernel(const HeaParams<float> p, const unsigned char* __restrict__ images
             };
             for (int64_t g = 0; g < NS - 1 && g < total; ++g) fetch(g);
             bool dead = false;
+            uint32_t apar = 0;
+            auto gemm = [&](uint32_t d, uint32_t a, uint32_t sb) {      // D = A_hi B_hi + A_hi B_lo + A_lo B_hi
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    tc::mma_f16_ts(d, a + 8u * j, tc::smem_desc_kmajor(sb + 256u * j, 128u, 1024u), idesc, j > 0);
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    tc::mma_f16_ts(d, a + 8u * j, tc::smem_desc_kmajor(sb + 8192u + 256u * j, 128u, 1024u), idesc, 1u);
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    tc::mma_f16_ts(d, a + 32u + 8u * j, tc::smem_desc_kmajor(sb + 256u * j, 128u, 1024u), idesc, 1u);
+            };
             for (int64_t g = 0; g < total; ++g) {
                 const int stage = (int)(g % NS);
                 const bool rev = GRAD && (int)(g % nsteps) >= p.K;
-                if (!dead && !tc_wait(bar_a_t, (uint32_t)(g & 1), err)) dead = true;
-                tc::tc_fence_after();
-                if (!dead && !tc_wait(tc::smem_u32(&bar_full[t][stage]), (uint32_t)((g / NS) & 1), err)) dead = true;
                 const uint32_t sb = ring + (uint32_t)stage * kTcImgBytes;
-                if (!dead) {
-                    const int nstate = rev ? 2 : 1;
-                    for (int v = 0; v < nstate; ++v) {
-                        const uint32_t d = mD + 64u * v, a = mA + 64u * v;
-#pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            tc::mma_f16_ts(d, a + 8u * j, tc::smem_desc_kmajor(sb + 256u * j, 128u, 1024u), idesc, j > 0);
-#pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            tc::mma_f16_ts(d, a + 8u * j, tc::smem_desc_kmajor(sb + 8192u + 256u * j, 128u, 1024u), idesc, 1u);
-#pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            tc::mma_f16_ts(d, a + 32u + 8u * j, tc::smem_desc_kmajor(sb + 256u * j, 128u, 1024u), idesc, 1u);
+                const int nsub = (SEQ && rev) ? 2 : 1;      // SEQ: psi and lam take turns through the one A / D pair
+                for (int v = 0; v < nsub; ++v) {
+                    if (!dead && !tc_wait(bar_a_t, apar, err)) dead = true;
+                    apar ^= 1u;
+                    tc::tc_fence_after();
+                    if (v == 0 && !dead && !tc_wait(tc::smem_u32(&bar_full[t][stage]), (uint32_t)((g / NS) & 1), err)) dead = true;
+                    if (!dead) {
+                        gemm(mD, mA, sb);
+                        if (!SEQ && rev) gemm(mD + 64u, mA + 64u, sb);
                     }
+                    tc::mma_commit(bar_d_t);
                 }
-                tc::mma_commit(bar_d_t);
                 // the stage of step g-1 is free: its MMAs completed before a_ready(g) could be signalled
                 if (g + NS - 1 < total) fetch(g + NS - 1);
             }
@@ -315,13 +327,13 @@ hea_tc_kernel(const HeaParams<float> p, const unsigned char* __restrict__ images
         __syncwarp();
     } else {
         // =================================================== compute warps
-        if constexpr (GRAD) asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");  // 168*384 = 232*256 + 40*128
+        if constexpr (GRAD) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(G::REGS_COMPUTE));
         const int t = warp >> 2, quarter = warp & 3;
         const uint32_t lane_sel = (uint32_t)(quarter * 32) << 16;
         const uint32_t tDp = tmem_base + lane_sel + (uint32_t)t * G::TILE_COLS;     // D psi
         const uint32_t tDl = tDp + 64u;                                              // D lam      (GRAD)
-        const uint32_t tAp = tDp + (GRAD ? 128u : 64u);                              // A psi: hi 32 | lo 32
-        const uint32_t tAl = tAp + 64u;                                              // A lam      (GRAD)
+        const uint32_t tAp = tDp + (GRAD && !SEQ ? 128u : 64u);                      // A psi: hi 32 | lo 32
+        const uint32_t tAl = tAp + 64u;                                              // A lam      (GRAD, !SEQ)
         const uint32_t bar_a_t = tc::smem_u32(&bar_a[t]), bar_d_t = tc::smem_u32(&bar_d[t]);
         uint32_t dpar = 0;
         bool dead = false;
@@ -517,14 +529,26 @@ hea_tc_kernel(const HeaParams<float> p, const unsigned char* __restrict__ images
                         const float tot = butterfly_reduce<float, 16>(mv, lane);
                         if ((lane & 1) == 0) atomicAdd(mrow + (int64_t)s * 16 + (lane >> 1), tot);
                         // un-apply the sublayer on both states
-                        tc_store_operand(tAp, ps);
-                        tc_store_operand(tAl, lm);
-                        signal_a();
                         float pr[16], pi[16];
-                        if (j == 0) tc_phase_table(th, 1.f, pr, pi);
-                        wait_d();
-                        tc_load_state(tDp, ps);
-                        tc_load_state(tDl, lm);
+                        if constexpr (!SEQ) {
+                            tc_store_operand(tAp, ps);
+                            tc_store_operand(tAl, lm);
+                            signal_a();
+                            if (j == 0) tc_phase_table(th, 1.f, pr, pi);
+                            wait_d();
+                            tc_load_state(tDp, ps);
+                            tc_load_state(tDl, lm);
+                        } else {
+                            tc_store_operand(tAp, ps);
+                            signal_a();
+                            if (j == 0) tc_phase_table(th, 1.f, pr, pi);
+                            wait_d();
+                            tc_load_state(tDp, ps);          // psi un-applied; the operand region is free again
+                            tc_store_operand(tAp, lm);
+                            signal_a();
+                            wait_d();
+                            tc_load_state(tDp, lm);
+                        }
                         if (DBG && dump) {
 #pragma unroll
                             for (int i = 0; i < 64; ++i) {

@@ -537,10 +537,14 @@ int make_plan(int64_t B, int n, int K, const int* depth, int dtype, int mode, Pl
     }
     if (dtype == QON_F32 && n == 5) {
         // the tensor-core tier (hea_tc2.cuh) writes one partial row per compute warp: 8 warps x min(SMs, ceil(B / 256)) CTAs
-        int64_t tcg = (B + 255) / 256;
+        // (2-tile layout) or 12 warps x min(SMs, ceil(B / 384)) CTAs (3-tile layout)
+        int64_t tcg = (B + 255) / 256, tcg3 = (B + 383) / 384;
         if (tcg > di.sms) tcg = di.sms;
+        if (tcg3 > di.sms) tcg3 = di.sms;
         if (tcg < 1) tcg = 1;
+        if (tcg3 < 1) tcg3 = 1;
         if (pl->rows < (int)tcg * 8) pl->rows = (int)tcg * 8;
+        if (pl->rows < (int)tcg3 * 12) pl->rows = (int)tcg3 * 12;
     }
     size_t off = 0;
     pl->off_u = off; off = align_up(off + (size_t)S * n * 4 * es);
@@ -661,7 +665,7 @@ int run(const Job& j) {
             if constexpr (sizeof(T) == 4) {
                 int dev; DeviceInfo di;
                 if (!device_info(&dev, &di)) return fail(QON_ERR_NO_DEVICE, "no usable CUDA device");
-                e = tc_launch(mode, tcc.enable == 2 ? 1 : 2, di.sms, (const HeaParams<float>&)p, (const float*)j.w, dp,
+                e = tc_launch(mode, tcc.enable == 2 ? 1 : (tcc.enable == 3 ? 3 : 2), di.sms, (const HeaParams<float>&)p, (const float*)j.w, dp,
                               base + pl.off_tc, tcc.dbg, tcc.err, st);
             } else e = cudaErrorInvalidValue;
         } else if (pl.fast_warp) {
