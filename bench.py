@@ -375,45 +375,21 @@ def run_b200(args):
         fwd_ms = f0.elapsed_time(f1) / 5
         del x_enc
 
-    # ---- end to end from pinned host memory (e2e)
+    # ---- end to end from pinned host memory (e2e), through the product API: DataParallelTrainer.run_host_fed
+    #      double-buffers the H2D copy of batch i+1 under the step of batch i and reads every step's loss back
     host = [synth_batch(B, seed=200 + rank + 7 * i, pin=True) for i in range(2)]
-    dbuf = [tuple(torch.empty_like(t, device=dev) for t in host[0]) for _ in range(2)]
-    copy_stream = torch.cuda.Stream(device=dev)
-    ready = [torch.cuda.Event() for _ in range(2)]
-    consumed = [torch.cuda.Event() for _ in range(2)]
-    loss_host = torch.empty(1, dtype=torch.float32).pin_memory()
 
-    def enqueue_copy(i):
-        slot = i % 2
-        with torch.cuda.stream(copy_stream):
-            copy_stream.wait_event(consumed[slot])
-            for d, h in zip(dbuf[slot], host[slot]):
-                d.copy_(h, non_blocking=True)
-            ready[slot].record(copy_stream)
-
-    def e2e_loop(n_steps):
-        cur = torch.cuda.current_stream()
-        for c in consumed:
-            c.record(cur)
-        enqueue_copy(0)
+    def host_batches(n_steps):
         for i in range(n_steps):
-            if i + 1 < n_steps:
-                enqueue_copy(i + 1)
-            slot = i % 2
-            cur.wait_event(ready[slot])
-            b_, t_, y_ = dbuf[slot]
-            l = trainer.step((b_, t_), y_)
-            consumed[slot].record(cur)
-            loss_host.copy_(l.reshape(1).float(), non_blocking=True)     # D2H read of the step's loss
-        torch.cuda.synchronize()
-        return float(loss_host[0])
+            b_, t_, y_ = host[i % 2]
+            yield (b_, t_), y_
 
-    e2e_loop(3)
+    trainer.run_host_fed(host_batches(3))
     aligned_start()
     g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
     g0.record()
-    e2e_loop(K)
+    e2e_losses = trainer.run_host_fed(host_batches(K))
     g1.record()
     torch.cuda.synchronize()
     wall_ms = (time.perf_counter() - t0) * 1e3
@@ -423,6 +399,7 @@ def run_b200(args):
     e2e_ms = max_over_ranks(max(g0.elapsed_time(g1), wall_ms))
     e2e_value = world * B * K / (e2e_ms * 1e-3)
     h2d = sum(t.numel() * t.element_size() for t in host[0])
+    assert len(e2e_losses) == K and all(v == v for v in e2e_losses)
 
     # ---- the reference's default batch (utils/common.py:128: 100 samples per step): the latency-bound point
     #      of SURVEY §8(e).  Eager steps at every N (all-reduce included); CUDA-graph replay of the step at N=1.
@@ -482,7 +459,8 @@ def run_b200(args):
             "config": bench_config(world, B, trainer.fused_encoding),
             "clocks": sampler.summary(),
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
-                    "ms_per_step": e2e_ms / K, "timer": "max(CUDA events, host wall clock) over the K steps, max over ranks"},
+                    "ms_per_step": e2e_ms / K, "api": "DataParallelTrainer.run_host_fed",
+                    "timer": "max(CUDA events, host wall clock) over the K steps, max over ranks"},
             # this library's kernels per step: prep, circuit kernel, finalize (+ finalize_enc) — with N > 1 the
             # finalize kernel is also the all-reduce (finalize_exchange_kernel), else one peer all-reduce kernel more;
             # the tensor-core tier adds its two operand-image prep kernels

@@ -6,11 +6,11 @@ namespace qon {
 
 size_t tc_workspace_bytes(int K, int S) { return (size_t)(K + S) * kTcImgBytes + 256; }
 
-template <bool GRAD, bool GX, int ENC, bool DBG, bool SEQ = false>
+template <bool GRAD, bool GX, int ENC, bool DBG>
 static cudaError_t tc_launch_t(int grid, const HeaParams<float>& p, const unsigned char* img, float* dbg, int* err,
                                cudaStream_t st) {
-    using G = TcGeom<GRAD, SEQ>;
-    auto kern = hea_tc_kernel<GRAD, GX, ENC, DBG, SEQ>;
+    using G = TcGeom<GRAD>;
+    auto kern = hea_tc_kernel<GRAD, GX, ENC, DBG>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM);
     if (e != cudaSuccess) return e;
     kern<<<grid, G::THREADS, G::SMEM, st>>>(p, img, dbg, err);
@@ -18,8 +18,7 @@ static cudaError_t tc_launch_t(int grid, const HeaParams<float>& p, const unsign
 }
 
 // mode: hea_reg_inst.cuh (0 fwd | 1 grad + dL/dx | 2 grad | 3 fwd, fused encoding | 4 grad, fused encoding |
-// 5 grad, fused encoding + frequency-layer gradients).  version 1 = the first forward kernel (hea_tc.cuh), kept for A/B;
-// version 3 = the 3-tile sequential layout of the gradient kernels (modes 2 and 5).
+// 5 grad, fused encoding + frequency-layer gradients).  version 1 = the first forward kernel (hea_tc.cuh), kept for A/B.
 cudaError_t tc_launch(int mode, int version, int sms, const HeaParams<float>& p, const float* w, const DepthPack& dp,
                       char* tc_ws, float* dbg, int* err_user, cudaStream_t st) {
     unsigned char* img = reinterpret_cast<unsigned char*>(tc_ws);
@@ -34,8 +33,7 @@ cudaError_t tc_launch(int mode, int version, int sms, const HeaParams<float>& p,
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     const int64_t ntiles = (p.B + 127) / 128;
-    const bool seq = grad && version == 3;
-    const int nt = grad ? (seq ? 3 : 2) : 4;
+    const int nt = grad ? 2 : 4;
     int64_t grid = (ntiles + nt - 1) / nt;
     if (grid > sms) grid = sms;
     if (grid < 1) grid = 1;
@@ -59,11 +57,9 @@ cudaError_t tc_launch(int mode, int version, int sms, const HeaParams<float>& p,
         case 3: return tc_launch_t<false, false, 1, false>(g, p, img, dbg, err, st);
         case 1: return dbg ? tc_launch_t<true, true, 0, true>(g, p, img, dbg, err, st)
                            : tc_launch_t<true, true, 0, false>(g, p, img, dbg, err, st);
-        case 2: return seq ? tc_launch_t<true, false, 0, false, true>(g, p, img, dbg, err, st)
-                           : tc_launch_t<true, false, 0, false>(g, p, img, dbg, err, st);
+        case 2: return tc_launch_t<true, false, 0, false>(g, p, img, dbg, err, st);
         case 4: return tc_launch_t<true, false, 1, false>(g, p, img, dbg, err, st);
-        case 5: return seq ? tc_launch_t<true, false, 2, false, true>(g, p, img, dbg, err, st)
-                           : tc_launch_t<true, false, 2, false>(g, p, img, dbg, err, st);
+        case 5: return tc_launch_t<true, false, 2, false>(g, p, img, dbg, err, st);
         default: return cudaErrorInvalidValue;
     }
 }

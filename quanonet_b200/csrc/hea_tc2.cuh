@@ -22,20 +22,16 @@
 
 namespace qon {
 
-// SEQ (gradient kernels only): 3 tiles of 128 TMEM columns each (one operand region A, one accumulator D); a reverse
-// step runs its two GEMMs one after the other through them (psi, then lam).  !SEQ: 2 tiles of 256 columns, both GEMMs
-// of a reverse step in flight at once.  More tiles = more warps to hide latencies; registers (psi + lam = 128 per
-// thread) cap the CTA at 12 compute warps.
-template <bool GRAD, bool SEQ = false> struct TcGeom {
-    static constexpr int NT = GRAD ? (SEQ ? 3 : 2) : 4;     // tiles per CTA
+template <bool GRAD> struct TcGeom {
+    static constexpr int NT = GRAD ? 2 : 4;                 // tiles per CTA
     static constexpr int NS = GRAD ? 4 : 3;                 // B-image ring stages per tile
     static constexpr int COMPUTE_WARPS = 4 * NT;
     static constexpr int WARPS = COMPUTE_WARPS + 4;         // + one warpgroup hosting the NT MMA warps
     static constexpr int THREADS = WARPS * 32;
-    static constexpr int TILE_COLS = GRAD && !SEQ ? 256 : 128;   // TMEM columns per tile
+    static constexpr int TILE_COLS = GRAD ? 256 : 128;      // TMEM columns per tile
     static constexpr int SMEM = NT * NS * kTcImgBytes;
-    // register hand-over (setmaxnreg) from the MMA warpgroup to the compute warps; both sum to 64K registers
-    static constexpr int REGS_COMPUTE = SEQ ? 160 : 232, REGS_MMA = SEQ ? 32 : 40;
+    // register hand-over (setmaxnreg) from the MMA warpgroup to the compute warps: 168 * 384 = 232 * 256 + 40 * 128
+    static constexpr int REGS_COMPUTE = 232, REGS_MMA = 40;
 };
 
 // a (.) P(z) + c with the operand patterns of ffma2.cuh applied to the packed operand z
@@ -57,7 +53,10 @@ __device__ __forceinline__ u64 tc_pair(const uint32_t (&r)[64], int z) {
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// prep of the reverse images: grid = S CTAs of 32 threads, image s' = S-1-s (execution order of the sweep)
+// prep of the reverse images: grid = S CTAs of 32 threads, image s' = S-1-s (execution order of the sweep).
+// Image of sublayer s (block k, sublayers s0 .. last): the COMPOSITE matrix taking the block's output cut to the cut
+// after sublayer s-1,  C_s = [H if s == s0] (R_s^+ Ring^+) ... (R_last^+ Ring^+) [H if k < K-1],
+// so one operand split per block serves all its GEMMs.
 // ---------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(32) tc_prep_rev_kernel(const float* __restrict__ w, int K, int S, DepthPack dp,
                                                          unsigned char* __restrict__ rimg) {
@@ -67,7 +66,7 @@ __global__ void __launch_bounds__(32) tc_prep_rev_kernel(const float* __restrict
     int k = 0, s0 = 0;
     while (s0 + dp.d[k] <= s) { s0 += dp.d[k]; ++k; }
     const bool first_in_block = s == s0;
-    const bool input_had = (s == s0 + dp.d[k] - 1) && (k < K - 1);
+    const bool input_had = k < K - 1;   // the operand is the block's OUTPUT cut, held in the Hadamard basis except for the last block
     const double h = 0.70710678118654752440;
     auto fwht = [&]() {
         for (int q = 0; q < n; ++q)
@@ -81,35 +80,37 @@ __global__ void __launch_bounds__(32) tc_prep_rev_kernel(const float* __restrict
     };
     for (int z = 0; z < N; ++z) { vr[z][j] = z == j ? 1.0 : 0.0; vi[z][j] = 0.0; }
     if (input_had) fwht();
-    for (int i = n - 1; i >= 0; --i) {   // Ring^+ : the CNOTs in reverse order
-        const int c = (i + 1) % n;
-        for (int z = 0; z < N; ++z) {
-            if (((z >> c) & 1) && !((z >> i) & 1)) {
-                const int z1 = z | (1 << i);
-                double t = vr[z][j]; vr[z][j] = vr[z1][j]; vr[z1][j] = t;
-                t = vi[z][j]; vi[z][j] = vi[z1][j]; vi[z1][j] = t;
+    for (int ss = s0 + dp.d[k] - 1; ss >= s; --ss) {   // un-apply the block's sublayers last .. s
+        for (int i = n - 1; i >= 0; --i) {   // Ring^+ : the CNOTs in reverse order
+            const int c = (i + 1) % n;
+            for (int z = 0; z < N; ++z) {
+                if (((z >> c) & 1) && !((z >> i) & 1)) {
+                    const int z1 = z | (1 << i);
+                    double t = vr[z][j]; vr[z][j] = vr[z1][j]; vr[z1][j] = t;
+                    t = vi[z][j]; vi[z][j] = vi[z1][j]; vi[z1][j] = t;
+                }
             }
         }
-    }
-    for (int q = 0; q < n; ++q) {
-        const double a = (double)w[((int64_t)s * 3 + 0) * n + q];
-        const double b = (double)w[((int64_t)s * 3 + 1) * n + q];
-        const double c = (double)w[((int64_t)s * 3 + 2) * n + q];
-        double sa, ca, sb, cb, sc, cc;
-        sincos(0.5 * a, &sa, &ca);
-        sincos(0.5 * b, &sb, &cb);
-        sincos(0.5 * c, &sc, &cc);
-        const double ar = cb * (cc * ca - sc * sa), ai = -sb * (cc * ca + sc * sa);
-        const double br = cb * (sc * ca + cc * sa), bi = sb * (cc * sa - sc * ca);
-        // U^+ = [[conj(al), conj(be)], [-be, al]]
-        for (int z = 0; z < N; ++z) {
-            if (z & (1 << q)) continue;
-            const int z1 = z | (1 << q);
-            const double x0r = vr[z][j], x0i = vi[z][j], x1r = vr[z1][j], x1i = vi[z1][j];
-            vr[z][j] = ar * x0r + ai * x0i + br * x1r + bi * x1i;
-            vi[z][j] = ar * x0i - ai * x0r + br * x1i - bi * x1r;
-            vr[z1][j] = -br * x0r + bi * x0i + ar * x1r - ai * x1i;
-            vi[z1][j] = -br * x0i - bi * x0r + ar * x1i + ai * x1r;
+        for (int q = 0; q < n; ++q) {
+            const double a = (double)w[((int64_t)ss * 3 + 0) * n + q];
+            const double b = (double)w[((int64_t)ss * 3 + 1) * n + q];
+            const double c = (double)w[((int64_t)ss * 3 + 2) * n + q];
+            double sa, ca, sb, cb, sc, cc;
+            sincos(0.5 * a, &sa, &ca);
+            sincos(0.5 * b, &sb, &cb);
+            sincos(0.5 * c, &sc, &cc);
+            const double ar = cb * (cc * ca - sc * sa), ai = -sb * (cc * ca + sc * sa);
+            const double br = cb * (sc * ca + cc * sa), bi = sb * (cc * sa - sc * ca);
+            // U^+ = [[conj(al), conj(be)], [-be, al]]
+            for (int z = 0; z < N; ++z) {
+                if (z & (1 << q)) continue;
+                const int z1 = z | (1 << q);
+                const double x0r = vr[z][j], x0i = vi[z][j], x1r = vr[z1][j], x1i = vi[z1][j];
+                vr[z][j] = ar * x0r + ai * x0i + br * x1r + bi * x1i;
+                vi[z][j] = ar * x0i - ai * x0r + br * x1i - bi * x1r;
+                vr[z1][j] = -br * x0r + bi * x0i + ar * x1r - ai * x1i;
+                vi[z1][j] = -br * x0i - bi * x0r + ar * x1i + ai * x1r;
+            }
         }
     }
     if (first_in_block) fwht();
@@ -147,19 +148,26 @@ __device__ __forceinline__ void tc_load_state(uint32_t taddr, uint32_t (&r)[64])
     tc::tmem_wait_ld();
 }
 
+// one amplitude (re, im) -> packed f16 hi and lo parts: hi = the 11 leading significant bits (mask), lo = x - hi (exact in
+// f32, one packed FFMA2), both converted with round-to-nearest
+__device__ __forceinline__ void tc_split(u64 x, uint32_t& ahi, uint32_t& alo) {
+    float xr, xi;
+    unpack2(x, xr, xi);
+    const float hr = __uint_as_float(__float_as_uint(xr) & 0xFFFFE000u);
+    const float hi_ = __uint_as_float(__float_as_uint(xi) & 0xFFFFE000u);
+    float lr, li;
+    unpack2(fma2<6>(1.f, pack2(hr, hi_), x), lr, li);      // x - h
+    ahi = tc::cvt_f16x2(hr, hi_);
+    alo = tc::cvt_f16x2(lr, li);
+}
+
 // registers (scaled state) -> f16 hi | lo operand rows at taddr (+0: hi, +32: lo)
 __device__ __forceinline__ void tc_store_operand(uint32_t taddr, const uint32_t (&r)[64]) {
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
         uint32_t ahi[8], alo[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const float xr = __uint_as_float(r[16 * c + 2 * i]), xi = __uint_as_float(r[16 * c + 2 * i + 1]);
-            const float hr = __uint_as_float(r[16 * c + 2 * i] & 0xFFFFE000u);
-            const float hi_ = __uint_as_float(r[16 * c + 2 * i + 1] & 0xFFFFE000u);
-            ahi[i] = tc::cvt_f16x2(hr, hi_);
-            alo[i] = tc::cvt_f16x2(xr - hr, xi - hi_);
-        }
+        for (int i = 0; i < 8; ++i) tc_split(tc_pair(r, 8 * c + i), ahi[i], alo[i]);
         tc::tmem_st8(taddr + 8u * c, ahi);
         tc::tmem_st8(taddr + 32u + 8u * c, alo);
     }
@@ -185,40 +193,46 @@ __device__ __forceinline__ void tc_apply_phases(uint32_t (&r)[64], const float (
 // Im <lam| T |psi> for the 15 strings of one cut type: mv[3q + {0,1,2}] = {X,Y,Z}_q moments
 template <bool HAD>
 __device__ __forceinline__ void tc_moments(const uint32_t (&ps)[64], const uint32_t (&lm)[64], float (&mv)[16]) {
-    static_for<15>([&](auto Tc) {
-        constexpr int T = decltype(Tc)::value;
-        constexpr TcString st = HAD ? kTcStrHad[T] : kTcStrComp[T];
-        u64 acc0 = 0ull, acc1 = 0ull;
-        static_for<32>([&](auto Zc) {
-            constexpr int zp = decltype(Zc)::value;
+    // 15 independent accumulation chains (one per string), the strings innermost: a chain's FFMA2s are 15
+    // instructions apart, so none waits on its predecessor
+    u64 acc[15];
+#pragma unroll
+    for (int T = 0; T < 15; ++T) acc[T] = 0ull;
+    static_for<32>([&](auto Zc) {
+        constexpr int zp = decltype(Zc)::value;
+        const u64 l = tc_pair(lm, zp);
+        static_for<15>([&](auto Tc) {
+            constexpr int T = decltype(Tc)::value;
+            constexpr TcString st = HAD ? kTcStrHad[T] : kTcStrComp[T];
             constexpr bool neg = tc_parity((zp ^ st.mx) & st.mz);
             // Im(i^k s c), c = conj(lam_zp) psi_{zp^mx}:  k=0: s Im c | 1: s Re c | 2: -s Im c | 3: -s Re c
             constexpr bool want_re = (st.k & 1) != 0;
             constexpr bool minus = neg != (st.k >= 2);
             constexpr int PAT = want_re ? (minus ? 6 : 0) : (minus ? 2 : 3);
-            const u64 l = tc_pair(lm, zp), pp = tc_pair(ps, zp ^ st.mx);
-            if constexpr (zp & 1) acc1 = fma2_vp<PAT>(l, pp, acc1);
-            else acc0 = fma2_vp<PAT>(l, pp, acc0);
+            acc[T] = fma2_vp<PAT>(l, tc_pair(ps, zp ^ st.mx), acc[T]);
         });
-        mv[T] = (lo2(acc0) + hi2(acc0)) + (lo2(acc1) + hi2(acc1));
     });
+#pragma unroll
+    for (int T = 0; T < 15; ++T) mv[T] = lo2(acc[T]) + hi2(acc[T]);
     mv[15] = 0.f;
 }
 
 // encoding-angle gradients: sum_z (1 - 2 z_q) Im(conj(mu_z) phi_z), q = 0..4
 __device__ __forceinline__ void tc_xgrad(const uint32_t (&ps)[64], const uint32_t (&lm)[64], float (&gq)[5]) {
-    static_for<5>([&](auto Qc) {
-        constexpr int q = decltype(Qc)::value;
-        u64 acc0 = 0ull, acc1 = 0ull;
-        static_for<32>([&](auto Zc) {
-            constexpr int z = decltype(Zc)::value;
-            constexpr bool neg = ((z >> q) & 1) != 0;
-            const u64 l = tc_pair(lm, z), pp = tc_pair(ps, z);
-            if constexpr (z & 1) acc1 = neg ? fma2_vp<2>(l, pp, acc1) : fma2_vp<3>(l, pp, acc1);
-            else acc0 = neg ? fma2_vp<2>(l, pp, acc0) : fma2_vp<3>(l, pp, acc0);
+    u64 acc[5];
+#pragma unroll
+    for (int q = 0; q < 5; ++q) acc[q] = 0ull;
+    static_for<32>([&](auto Zc) {
+        constexpr int z = decltype(Zc)::value;
+        const u64 l = tc_pair(lm, z), pp = tc_pair(ps, z);
+        static_for<5>([&](auto Qc) {
+            constexpr int q = decltype(Qc)::value;
+            if constexpr (((z >> q) & 1) != 0) acc[q] = fma2_vp<2>(l, pp, acc[q]);
+            else acc[q] = fma2_vp<3>(l, pp, acc[q]);
         });
-        gq[q] = (lo2(acc0) + hi2(acc0)) + (lo2(acc1) + hi2(acc1));
     });
+#pragma unroll
+    for (int q = 0; q < 5; ++q) gq[q] = lo2(acc[q]) + hi2(acc[q]);
 }
 
 // bounded mbarrier wait without busy work: try_wait suspends in hardware for up to ~20 us per probe
@@ -241,11 +255,10 @@ __device__ __forceinline__ bool tc_wait(uint32_t bar, uint32_t parity, int* err)
 // the kernel.  ENC as in hea_reg.cuh (0: x given, 1: fused encoding, 2: + frequency-layer gradients)
 // images: [K forward block images | S reverse sublayer images in sweep order]
 // ---------------------------------------------------------------------------------------------------------
-template <bool GRAD, bool NEED_GX, int ENC, bool DBG, bool SEQ>
-__global__ void __launch_bounds__(TcGeom<GRAD, SEQ>::THREADS, 1)
+template <bool GRAD, bool NEED_GX, int ENC, bool DBG>
+__global__ void __launch_bounds__(TcGeom<GRAD>::THREADS, 1)
 hea_tc_kernel(const HeaParams<float> p, const unsigned char* __restrict__ images, float* dbg, int* err) {
-    using G = TcGeom<GRAD, SEQ>;
-    static_assert(GRAD || !SEQ, "SEQ is a gradient-kernel layout");
+    using G = TcGeom<GRAD>;
     constexpr int NQ = 5, NT = G::NT, NS = G::NS;
     constexpr bool FREQ_GRAD = GRAD && ENC == 2;
     constexpr bool WANT_GX = NEED_GX || FREQ_GRAD;
@@ -279,7 +292,7 @@ hea_tc_kernel(const HeaParams<float> p, const unsigned char* __restrict__ images
         const int t = warp - G::COMPUTE_WARPS;
         if (t < NT && lane == 0) {
             const uint32_t mD = tmem_base + (uint32_t)t * G::TILE_COLS;
-            const uint32_t mA = mD + (GRAD && !SEQ ? 128u : 64u);
+            const uint32_t mA = mD + (GRAD ? 128u : 64u);
             const uint32_t ring = tc::smem_u32(tc_smem + (size_t)t * NS * kTcImgBytes);
             const uint32_t bar_a_t = tc::smem_u32(&bar_a[t]), bar_d_t = tc::smem_u32(&bar_d[t]);
             constexpr uint32_t idesc = tc::idesc_f16(128, 64);
@@ -308,18 +321,15 @@ hea_tc_kernel(const HeaParams<float> p, const unsigned char* __restrict__ images
                 const int stage = (int)(g % NS);
                 const bool rev = GRAD && (int)(g % nsteps) >= p.K;
                 const uint32_t sb = ring + (uint32_t)stage * kTcImgBytes;
-                const int nsub = (SEQ && rev) ? 2 : 1;      // SEQ: psi and lam take turns through the one A / D pair
-                for (int v = 0; v < nsub; ++v) {
-                    if (!dead && !tc_wait(bar_a_t, apar, err)) dead = true;
-                    apar ^= 1u;
-                    tc::tc_fence_after();
-                    if (v == 0 && !dead && !tc_wait(tc::smem_u32(&bar_full[t][stage]), (uint32_t)((g / NS) & 1), err)) dead = true;
-                    if (!dead) {
-                        gemm(mD, mA, sb);
-                        if (!SEQ && rev) gemm(mD + 64u, mA + 64u, sb);
-                    }
-                    tc::mma_commit(bar_d_t);
+                if (!dead && !tc_wait(bar_a_t, apar, err)) dead = true;
+                apar ^= 1u;
+                tc::tc_fence_after();
+                if (!dead && !tc_wait(tc::smem_u32(&bar_full[t][stage]), (uint32_t)((g / NS) & 1), err)) dead = true;
+                if (!dead) {
+                    gemm(mD, mA, sb);
+                    if (rev) gemm(mD + 64u, mA + 64u, sb);
                 }
+                tc::mma_commit(bar_d_t);
                 // the stage of step g-1 is free: its MMAs completed before a_ready(g) could be signalled
                 if (g + NS - 1 < total) fetch(g + NS - 1);
             }
@@ -332,8 +342,8 @@ hea_tc_kernel(const HeaParams<float> p, const unsigned char* __restrict__ images
         const uint32_t lane_sel = (uint32_t)(quarter * 32) << 16;
         const uint32_t tDp = tmem_base + lane_sel + (uint32_t)t * G::TILE_COLS;     // D psi
         const uint32_t tDl = tDp + 64u;                                              // D lam      (GRAD)
-        const uint32_t tAp = tDp + (GRAD && !SEQ ? 128u : 64u);                      // A psi: hi 32 | lo 32
-        const uint32_t tAl = tAp + 64u;                                              // A lam      (GRAD, !SEQ)
+        const uint32_t tAp = tDp + (GRAD ? 128u : 64u);                              // A psi: hi 32 | lo 32
+        const uint32_t tAl = tAp + 64u;                                              // A lam      (GRAD)
         const uint32_t bar_a_t = tc::smem_u32(&bar_a[t]), bar_d_t = tc::smem_u32(&bar_d[t]);
         uint32_t dpar = 0;
         bool dead = false;
@@ -342,7 +352,7 @@ hea_tc_kernel(const HeaParams<float> p, const unsigned char* __restrict__ images
             dpar ^= 1u;
             tc::tc_fence_after();
         };
-        auto signal_a = [&]() {
+        auto signal_a = [&]() {      // "operand written" / "accumulator drained": the MMA warp may issue the next step
             tc::tmem_wait_st();
             tc::tc_fence_before();
             __syncwarp();
@@ -422,12 +432,7 @@ hea_tc_kernel(const HeaParams<float> p, const unsigned char* __restrict__ images
                             nv = mul2<0>(pr[31 - z], v);
                             nv = fma2<3>(pi[31 - z], v, nv);
                         }
-                        float xr, xi;
-                        unpack2(nv, xr, xi);
-                        const float hr = __uint_as_float(__float_as_uint(xr) & 0xFFFFE000u);
-                        const float hi_ = __uint_as_float(__float_as_uint(xi) & 0xFFFFE000u);
-                        ahi[i] = tc::cvt_f16x2(hr, hi_);
-                        alo[i] = tc::cvt_f16x2(xr - hr, xi - hi_);
+                        tc_split(nv, ahi[i], alo[i]);
                     }
                     tc::tmem_st8(tAp + 8u * c, ahi);
                     tc::tmem_st8(tAp + 32u + 8u * c, alo);
@@ -518,6 +523,12 @@ hea_tc_kernel(const HeaParams<float> p, const unsigned char* __restrict__ images
                     float thn[NQ];
                     load_angles(k > 0 ? k - 1 : 0, thn);
                     const int d = __ldg(p.depth + k);
+                    // (ps, lm) = the block's output cut.  ONE operand split per block: every cut inside the block is a
+                    // GEMM of this operand with a composite matrix (prep), so the GEMM producing cut s-1 runs while the
+                    // CUDA cores measure the moments of cut s.
+                    tc_store_operand(tAp, ps);
+                    tc_store_operand(tAl, lm);
+                    signal_a();
                     for (int j = d - 1; j >= 0; --j, ++step) {
                         --s;
                         // Pauli moments of sublayer s on the cut held in registers, scaled by this sample's g
@@ -528,27 +539,12 @@ hea_tc_kernel(const HeaParams<float> p, const unsigned char* __restrict__ images
                         for (int i = 0; i < 15; ++i) mv[i] *= glam;
                         const float tot = butterfly_reduce<float, 16>(mv, lane);
                         if ((lane & 1) == 0) atomicAdd(mrow + (int64_t)s * 16 + (lane >> 1), tot);
-                        // un-apply the sublayer on both states
                         float pr[16], pi[16];
-                        if constexpr (!SEQ) {
-                            tc_store_operand(tAp, ps);
-                            tc_store_operand(tAl, lm);
-                            signal_a();
-                            if (j == 0) tc_phase_table(th, 1.f, pr, pi);
-                            wait_d();
-                            tc_load_state(tDp, ps);
-                            tc_load_state(tDl, lm);
-                        } else {
-                            tc_store_operand(tAp, ps);
-                            signal_a();
-                            if (j == 0) tc_phase_table(th, 1.f, pr, pi);
-                            wait_d();
-                            tc_load_state(tDp, ps);          // psi un-applied; the operand region is free again
-                            tc_store_operand(tAp, lm);
-                            signal_a();
-                            wait_d();
-                            tc_load_state(tDp, lm);
-                        }
+                        if (j == 0) tc_phase_table(th, 1.f, pr, pi);
+                        wait_d();
+                        tc_load_state(tDp, ps);
+                        tc_load_state(tDl, lm);
+                        if (j > 0) signal_a();        // accumulators drained: next composite of this block
                         if (DBG && dump) {
 #pragma unroll
                             for (int i = 0; i < 64; ++i) {

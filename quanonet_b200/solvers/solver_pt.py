@@ -50,13 +50,22 @@ class B200Solver:
             raise NotImplementedError("LBFGS requires a closure; not supported by the current training loop.")
         # single-process CUDA runs replay each full-size batch as ONE CUDA graph (static batch buffers): at the
         # reference's default batch_size = 100 a step is launch-latency bound (~0.6 ms eager, ~0.33 ms replayed)
-        self.use_graph = (bool(config.get("cuda_graph", True)) and self.device.type == "cuda" and self.world == 1
+        self.use_graph = (bool(config.get("cuda_graph", True)) and self.device.type == "cuda"
                           and opt_name in ("adam", "adamw", "sgd"))
         opt_kw = dict(config.get("optimizer_kwargs", {}))
+        lr = config["learning_rate"]
+        self._lr_in_graph = False
         if self.use_graph and opt_name in ("adam", "adamw"):
             opt_kw.setdefault("capturable", True)
-        self.trainer = DataParallelTrainer(self.model, lr=config["learning_rate"], optimizer=opt_name,
-                                           optimizer_kwargs=opt_kw)
+            # a TENSOR learning rate is read at replay time: a scheduler then never forces a re-capture
+            lr = torch.tensor(float(lr), dtype=torch.float32, device=self.device)
+            self._lr_in_graph = True
+        self.trainer = DataParallelTrainer(self.model, lr=lr, optimizer=opt_name, optimizer_kwargs=opt_kw)
+        if self.world > 1:
+            # replaying the step under torch.distributed needs an exchange that is itself graph-replayable and a batch
+            # that splits evenly: the library's peer-memory exchange (csrc/qon_peer.cuh keeps its epoch on the device)
+            from ..comm import PeerAllReduce
+            self.use_graph = self.use_graph and isinstance(self.trainer._all_reduce, PeerAllReduce)
         self.scheduler = self._build_scheduler()
         self.best_loss = float("inf")
         self.best_model_path = None
@@ -106,16 +115,18 @@ class B200Solver:
         gen = torch.Generator(device=self.device)
         gen.manual_seed(int(self.config.get("seed", 0)))       # same permutation on every rank
         graph = None
-        if self.use_graph:
-            static_in = tuple(torch.empty((bs,) + tuple(a.shape[1:]), dtype=a.dtype, device=self.device)
+        use_graph = self.use_graph and bs % self.world == 0
+        sb = bs // self.world if use_graph else bs                # this rank's shard of a full batch
+        if use_graph:
+            static_in = tuple(torch.empty((sb,) + tuple(a.shape[1:]), dtype=a.dtype, device=self.device)
                               for a in self.train_in)
-            static_y = torch.empty((bs, 1), dtype=self.train_out.dtype, device=self.device)
+            static_y = torch.empty((sb, 1), dtype=self.train_out.dtype, device=self.device)
 
         def capture():
             """(Re)capture one full-batch training step on the static buffers."""
             for dst, src in zip(static_in, self.train_in):
-                dst.copy_(src[:bs])
-            static_y.copy_(self.train_out[:bs])
+                dst.copy_(src[:sb])
+            static_y.copy_(self.train_out[:sb])
             saved = {k: v.clone() for k, v in self.model.state_dict().items()}
             opt = self.trainer.optimizer
             params = [p for g_ in opt.param_groups for p in g_["params"]]
@@ -142,8 +153,8 @@ class B200Solver:
 
         for epoch in range(epochs):
             self.model.train()
-            if self.use_graph and (graph is None or self.scheduler is not None):
-                graph, loss_static = capture()                # lr is baked into the graph: recapture when it moves
+            if use_graph and (graph is None or (self.scheduler is not None and not self._lr_in_graph)):
+                graph, loss_static = capture()                # a float lr is baked into the graph: recapture when it moves
             perm = torch.randperm(n, device=self.device, generator=gen)
             loss_sum = torch.zeros((), device=self.device)
             sse = torch.zeros((), device=self.device)
@@ -151,9 +162,10 @@ class B200Solver:
                 idx = perm[i * bs:(i + 1) * bs]
                 gb = idx.numel()
                 if graph is not None and gb == bs:
+                    ridx = idx[self.rank::self.world] if self.world > 1 else idx
                     for dst, src in zip(static_in, self.train_in):
-                        torch.index_select(src, 0, idx, out=dst)
-                    torch.index_select(self.train_out, 0, idx, out=static_y)
+                        torch.index_select(src, 0, ridx, out=dst)
+                    torch.index_select(self.train_out, 0, ridx, out=static_y)
                     graph.replay()
                     loss = loss_static
                 else:

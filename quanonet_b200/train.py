@@ -108,6 +108,7 @@ class DataParallelTrainer:
         if self.distributed:                               # replicas must start identical
             for p in model.parameters():
                 dist.broadcast(p.data, src=0, group=process_group)
+        self._views = [(p, p.data_ptr(), p.grad.data_ptr()) for p in ordered]
         # the exchange step: the library's one-kernel NVLink peer-memory all-reduce on CUDA/NCCL groups
         # (quanonet_b200/comm.py), torch.distributed's all_reduce elsewhere (gloo in the CPU tests)
         self._all_reduce = None
@@ -261,10 +262,72 @@ class DataParallelTrainer:
             self._all_reduce(fg)
         return fg[self.sse_idx] / gB
 
+    def _check_views(self):
+        """``model.to(...)`` / ``.double()`` / ``.cuda()`` after construction re-allocates the parameters and silently
+        detaches them from the flat buffers the kernels and the optimiser work on: refuse to train on such a model."""
+        for p, ptr, gptr in self._views:
+            if p.data_ptr() != ptr or p.grad is None or p.grad.data_ptr() != gptr:
+                raise RuntimeError(
+                    "the model's parameters no longer alias the trainer's flat buffers (was the model moved or cast with "
+                    ".to()/.cuda()/.double(), or were its gradients set to None, after DataParallelTrainer was built?). "
+                    "Move the model first, then construct the trainer; use optimizer.zero_grad(set_to_none=False).")
+
     def step(self, inputs, y, global_batch=None):
+        self._check_views()
         loss = self.compute_grads(inputs, y, global_batch)
         self.optimizer.step()
         return loss
+
+    def run_host_fed(self, batches, global_batch=None, on_loss=None):
+        """Train on batches that live in HOST memory: ``batches`` yields ``(inputs, y)`` with ``inputs`` a tuple of CPU
+        tensors (pinned memory for asynchronous copies: ``tensor.pin_memory()``).  The copy of batch i+1 to the GPU
+        runs on its own stream while batch i trains (two device slots); every step's loss is copied back to a pinned
+        host scalar without stalling the stream.  Returns the list of per-step losses (floats) after one final sync —
+        the data path of a dataset larger than HBM, and what bench.py's ``e2e`` times.  ``on_loss(i, pinned_scalar)``
+        may be given to consume losses as they land."""
+        dev = self.flat_param.device
+        if dev.type != "cuda":
+            raise RuntimeError("run_host_fed needs the model on a CUDA device")
+        cur = torch.cuda.current_stream(dev)
+        copy_stream = torch.cuda.Stream(device=dev)
+        slots, ready, consumed = [None, None], [torch.cuda.Event(), torch.cuda.Event()], [torch.cuda.Event(), torch.cuda.Event()]
+        for c in consumed:
+            c.record(cur)
+        losses = []
+
+        def enqueue(slot, inputs, y):
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(consumed[slot])            # the step that last read this slot is done
+                if slots[slot] is None or any(d.shape != h.shape for d, h in zip(slots[slot], (*inputs, y))):
+                    slots[slot] = tuple(torch.empty(h.shape, dtype=h.dtype, device=dev) for h in (*inputs, y))
+                for d, h in zip(slots[slot], (*inputs, y)):
+                    d.copy_(h, non_blocking=True)
+                ready[slot].record(copy_stream)
+
+        it = iter(batches)
+        nxt = next(it, None)
+        i = 0
+        if nxt is not None:
+            enqueue(0, *nxt)
+        while nxt is not None:
+            slot = i % 2
+            nxt = next(it, None)
+            if nxt is not None:
+                enqueue((i + 1) % 2, *nxt)
+            cur.wait_event(ready[slot])
+            *ins, yy = slots[slot]
+            loss = self.step(tuple(ins), yy, global_batch)
+            consumed[slot].record(cur)
+            if i % 1024 == 0:                                      # pinned landing zone for the losses, 4 KB at a time
+                chunk = torch.empty(1024, dtype=torch.float32).pin_memory()
+            host = chunk[i % 1024:i % 1024 + 1]
+            host.copy_(loss.detach().reshape(1).float(), non_blocking=True)
+            losses.append(host)
+            if on_loss is not None:
+                on_loss(i, host)
+            i += 1
+        torch.cuda.synchronize(dev)
+        return [float(h[0]) for h in losses]
 
     def exchange_timed_out(self) -> bool:
         """True if the peer-memory exchange ever gave up waiting for a rank (~30 s): the gradients of that step were

@@ -91,7 +91,11 @@ def expected_steps(x, w, depths, hdiag):
     s = 0
     for k, d in enumerate(depths):
         first[s] = True; blk[s:s + d] = k; last[s + d - 1] = True; s += d
-    Gs = [emub.rev_matrix(w, s, first[s], last[s] and blk[s] < K - 1) for s in range(S)]
+    lastof = np.zeros(S, int)
+    s = 0
+    for k, d in enumerate(depths):
+        lastof[s:s + d] = s + d - 1; s += d
+    Gs = [emub.rev_matrix(w, s, lastof[s], first[s], blk[s] < K - 1) for s in range(S)]
     steps = [[np.zeros((B, 64)), np.zeros((B, 64))] for _ in range(K + S)]
     il = lambda v: np.stack([v.real, v.imag], -1).reshape(-1)
     for b in range(B):
@@ -103,7 +107,9 @@ def expected_steps(x, w, depths, hdiag):
         psi, lam = amp, hdiag * amp
         st = K
         for s in reversed(range(S)):
-            psi, lam = Gs[s] @ psi, Gs[s] @ lam
+            if last[s]:
+                opsi, olam = psi, lam
+            psi, lam = Gs[s] @ opsi, Gs[s] @ olam
             steps[st][0][b], steps[st][1][b] = il(psi), il(lam)
             st += 1
             if first[s]:

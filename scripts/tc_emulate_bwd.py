@@ -37,28 +37,30 @@ def fwht(v):
     return v
 
 
-def rev_matrix(w, s, first_in_block, input_had):
-    """G_s = [H if first-in-block] R_s^+ Ring^+ [H if the input cut is held in the Hadamard basis]"""
+def rev_matrix(w, s, last, first_in_block, input_had):
+    """Composite C_s = [H if first-in-block] (R_s^+ Ring^+) ... (R_last^+ Ring^+) [H if the block's output cut is held
+    in the Hadamard basis]: takes the block's OUTPUT cut to the cut after sublayer s-1."""
     G = np.zeros((N, N), complex)
     for j in range(N):
         v = np.zeros(N, complex); v[j] = 1
         if input_had:
             v = fwht(v)
-        for i in reversed(range(n)):
-            c = (i + 1) % n
-            for z in range(N):
-                if ((z >> c) & 1) and not ((z >> i) & 1):
-                    z1 = z | (1 << i)
-                    v[z], v[z1] = v[z1], v[z]
-        for q in range(n):
-            al, be = emu.su2(w[s, 0, q], w[s, 1, q], w[s, 2, q])
-            for z in range(N):
-                if z & (1 << q):
-                    continue
-                z1 = z | (1 << q)
-                x0, x1 = v[z], v[z1]
-                v[z] = np.conj(al) * x0 + np.conj(be) * x1
-                v[z1] = -be * x0 + al * x1
+        for ss in range(last, s - 1, -1):
+            for i in reversed(range(n)):
+                c = (i + 1) % n
+                for z in range(N):
+                    if ((z >> c) & 1) and not ((z >> i) & 1):
+                        z1 = z | (1 << i)
+                        v[z], v[z1] = v[z1], v[z]
+            for q in range(n):
+                al, be = emu.su2(w[ss, 0, q], w[ss, 1, q], w[ss, 2, q])
+                for z in range(N):
+                    if z & (1 << q):
+                        continue
+                    z1 = z | (1 << q)
+                    x0, x1 = v[z], v[z1]
+                    v[z] = np.conj(al) * x0 + np.conj(be) * x1
+                    v[z1] = -be * x0 + al * x1
         if first_in_block:
             v = fwht(v)
         G[:, j] = v
@@ -85,7 +87,11 @@ def tc_backward(x, w, depths, hdiag, gout):
     s = 0
     for k, d in enumerate(depths):
         first[s] = True; blk[s:s + d] = k; last[s + d - 1] = True; s += d
-    Gs = [rev_matrix(w, s, first[s], last[s] and blk[s] < K - 1) for s in range(S)]
+    lastof = np.zeros(S, int)
+    s = 0
+    for k, d in enumerate(depths):
+        lastof[s:s + d] = s + d - 1; s += d
+    Gs = [rev_matrix(w, s, lastof[s], first[s], blk[s] < K - 1) for s in range(S)]
     out = np.zeros(B); gx = np.zeros((B, n * K)); mom = np.zeros((S, 15))
     for b in range(B):
         amp = np.full(N, 1 / np.sqrt(N), complex)
@@ -99,8 +105,10 @@ def tc_backward(x, w, depths, hdiag, gout):
         psi, lam = amp, gout[b] * hdiag * amp
         for s in reversed(range(S)):
             had = last[s] and blk[s] < K - 1
+            if last[s]:
+                opsi, olam = psi, lam          # the block's output cut: operand of every GEMM of the block
             mom[s] += moments(psi, lam, STR["kTcStrHad"] if had else STR["kTcStrComp"])
-            psi, lam = Gs[s] @ psi, Gs[s] @ lam
+            psi, lam = Gs[s] @ opsi, Gs[s] @ olam
             if first[s]:
                 k = blk[s]
                 wz = np.imag(np.conj(lam) * psi)
