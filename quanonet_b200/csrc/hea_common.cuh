@@ -73,9 +73,9 @@ __host__ __device__ constexpr int moment_slots(int n) { return next_pow2(3 * n) 
 // ~300 RX gates of a circuit and costs ~2.5x in end-to-end accuracy (measured: 7.6e-6 -> 2.9e-6
 // rel-L2 vs the fp64 oracle at Q5 Net40-2-20-2).  Cody-Waite reduction by pi/2 with FMAs, minimax
 // polynomials on [-pi/4, pi/4] (sin: rel 3.6e-9, cos: abs 9.6e-11), quadrant fix-up by bit tricks.
-__device__ __forceinline__ void sincos_half(float t, float& s, float& c) {
+// branch-free core, valid for |t/2| <= 32768 (three-part Cody-Waite reduction stays exact up to there)
+__device__ __forceinline__ void sincos_half_fast(float t, float& s, float& c) {
     const float h = 0.5f * t;
-    if (__builtin_expect(fabsf(h) > 32768.0f, 0)) { sincosf(h, &s, &c); return; }   // Payne-Hanek territory
     const float kf = rintf(h * 0.636619772367581343f);
     const int k = __float2int_rn(kf);
     float r = fmaf(kf, -1.57079601287841796875f, h);          // pi/2 split in three parts
@@ -93,6 +93,10 @@ __device__ __forceinline__ void sincos_half(float t, float& s, float& c) {
     const float cc = (k & 1) ? sr : cr;
     s = __int_as_float(__float_as_int(ss) ^ ((k & 2) << 30));
     c = __int_as_float(__float_as_int(cc) ^ (((k + 1) & 2) << 30));
+}
+__device__ __forceinline__ void sincos_half(float t, float& s, float& c) {
+    if (__builtin_expect(fabsf(t) > 65536.0f, 0)) { sincosf(0.5f * t, &s, &c); return; }   // Payne-Hanek territory
+    sincos_half_fast(t, s, c);
 }
 __device__ __forceinline__ void sincos_half(double t, double& s, double& c) { sincos(0.5 * t, &s, &c); }
 

@@ -136,8 +136,15 @@ __device__ __forceinline__ void tc_cmul(float ar, float ai, float br, float bi, 
 
 __device__ __forceinline__ void tc_phase_table(const float (&th)[5], float scale, float (&pr)[16], float (&pi)[16]) {
     float s[5], c[5];
+    // five independent branch-free evaluations (one basic block: the scheduler interleaves them); the rare huge
+    // angle takes the accurate slow path afterwards
+    float big = 0.f;
 #pragma unroll
-    for (int q = 0; q < 5; ++q) sincos_half(th[q], s[q], c[q]);
+    for (int q = 0; q < 5; ++q) { sincos_half_fast(th[q], s[q], c[q]); big = fmaxf(big, fabsf(th[q])); }
+    if (__builtin_expect(big > 65536.0f, 0)) {
+#pragma unroll
+        for (int q = 0; q < 5; ++q) sincos_half(th[q], s[q], c[q]);
+    }
     // qubits 0..2: l[z2 z1 z0]; l[7 - j] = conj(l[j])
     float lr[4], li[4];
     {
