@@ -23,10 +23,24 @@ int tile_bits(bool reverse) {
     return reverse ? r : f;
 }
 
+// first qubit of pass B: pass A takes all TB low qubits.  A balanced split (QON_HBM_SPLIT=8 at n = 16: 8 fused gates
+// per pass instead of 13 + 3) was measured and is SLOWER (forward 53.6 vs 49.7 ms at n = 16, B = 1,184; equal at
+// n = 14 / 18): pass B's tiles then gather 128-byte chunks and the streaming phases, not the gates, bound both passes
+// (profiles/r2_hbm_split_ab.md).  The override stays for experiments; the tile index is general.
+int split_qubit(int n, int tb) {
+    static const int ov = [] { const char* e = getenv("QON_HBM_SPLIT"); return e ? atoi(e) : 0; }();
+    int qa = ov > 0 ? ov : tb;
+    if (qa > tb) qa = tb;                 // pass A's tile holds qubits 0..TB-1
+    if (qa < n - tb) qa = n - tb;         // pass B's tile holds at most TB qubits
+    if (qa < 1) qa = 1;
+    return qa;
+}
+
 void make_pass(HbmPass& hp, int n, int tb, bool passB, bool reverse) {
+    const int qa = split_qubit(n, tb);
     hp.n = n;
-    hp.c = passB ? 2 * tb - n : tb;
-    hp.qoff = passB ? tb - hp.c : 0;
+    hp.c = passB ? tb - (n - qa) : tb;
+    hp.qoff = passB ? n - tb : 0;     // qubit of local bit l >= c in pass B: l - c + qa = l + (n - tb)
     const int lo2 = smem_lo(tb, 2);
     int wins[3], masks[3], cnt = 0;
     for (int pw = 0; pw < 3; ++pw) {
@@ -35,7 +49,7 @@ void make_pass(HbmPass& hp, int n, int tb, bool passB, bool reverse) {
         for (int r = 0; r < 5; ++r) {
             const int l = lo + r;
             bool gated;
-            if (!passB) gated = pw < 2 ? true : l >= 10;                        // pass A: every local bit once
+            if (!passB) gated = (pw < 2 ? true : l >= 10) && l < qa;            // pass A: local bits [0, qa) once
             else gated = l >= hp.c && (pw == 2 || l < (pw == 1 ? lo2 : 5));     // pass B: local bits [c, TB) once
             if (gated) m |= 1 << r;
         }
@@ -49,7 +63,7 @@ void make_pass(HbmPass& hp, int n, int tb, bool passB, bool reverse) {
     }
     for (int bit = 0; bit < kMaxTileBits; ++bit) {
         unsigned g = 0;
-        if (bit < tb) g = tb == 13 ? hbm_gidx<13>(1u << bit, 0u, hp.c) : hbm_gidx<12>(1u << bit, 0u, hp.c);
+        if (bit < tb) g = tb == 13 ? hbm_gidx<13>(1u << bit, 0u, hp.c, n) : hbm_gidx<12>(1u << bit, 0u, hp.c, n);
         hp.ringp[bit] = bit < tb ? hbm_ring(g, n) : 0u;
     }
 }

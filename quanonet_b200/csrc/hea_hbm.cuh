@@ -3,10 +3,13 @@
 // that with lam in the reverse sweep).  One ansatz sublayer = TWO passes over HBM, each a kernel launch
 // over all tiles of the chunk:
 //
-//   pass A  tile = 2^TB contiguous amplitudes           -> gates on qubits 0..TB-1 (windows [0,5) [5,10) [TB-5,TB))
-//   pass B  tile = 2^c-amplitude contiguous chunks x the n-TB high qubits (c = 2 TB - n)
-//                                                       -> gates on qubits TB..n-1, then the CNOT ring as a
+//   pass A  tile = 2^TB contiguous amplitudes           -> gates on qubits 0..qa-1 (windows [0,5) [5,10) [TB-5,TB))
+//   pass B  tile = 2^c-amplitude contiguous chunks x the TB-c highest qubits (c = TB - (n - qa))
+//                                                       -> gates on qubits qa..n-1, then the CNOT ring as a
 //                                                          GF(2)-linear scatter on the way back to HBM
+// The split point qa balances the two passes (round 1 gave pass A all TB low qubits: at n = 16 that is 13 fused
+// gates per 1 MB of traffic — FP32-bound at any efficiency — against 3 gates in the HBM-bound pass B; with qa = 8
+// both passes carry 8 gates).
 //
 // Inside a tile the register-blocked FFMA2 window passes of the shared-memory tier (hea_smem.cuh) are reused
 // (same swizzle, same constant-memory offset tables, n = TB geometry, 2^(TB-5) threads per tile); windows
@@ -69,10 +72,11 @@ __host__ __device__ __forceinline__ unsigned hbm_ring(unsigned k, int n) {
     for (int i = 0; i < n; ++i) k ^= ((k >> (i + 1 == n ? 0 : i + 1)) & 1u) << i;
     return k;
 }
-// global amplitude index of local index l in tile t (TB-bit tiles)
+// global amplitude index of local index l in tile t (TB-bit tiles of an n-qubit state): the tile holds the c lowest
+// index bits and the TB - c highest; the n - TB bits in between enumerate the tiles
 template <int TB>
-__host__ __device__ __forceinline__ unsigned hbm_gidx(unsigned l, unsigned t, int c) {
-    return (l & ((1u << c) - 1u)) | (t << c) | ((l >> c) << TB);
+__host__ __device__ __forceinline__ unsigned hbm_gidx(unsigned l, unsigned t, int c, int n) {
+    return (l & ((1u << c) - 1u)) | (t << c) | ((l >> c) << (c + n - TB));
 }
 
 template <bool REVERSE, int TB>
@@ -101,7 +105,7 @@ hea_hbm_pass_kernel(const HeaParams<float> p, const HbmPass hp, const HbmBuffers
     };
     // ring(gidx(l)) is GF(2)-linear in l = tid + THREADS * r: thread part once per tile, r part = constants
     auto ring_base = [&](unsigned t) -> unsigned {
-        unsigned v = hbm_ring(hbm_gidx<TB>(0u, t, c), n);
+        unsigned v = hbm_ring(hbm_gidx<TB>(0u, t, c, n), n);
 #pragma unroll
         for (int bit = 0; bit < TIDB; ++bit)
             if ((tid >> bit) & 1) v ^= hp.ringp[bit];
@@ -131,7 +135,7 @@ hea_hbm_pass_kernel(const HeaParams<float> p, const HbmPass hp, const HbmBuffers
                     for (int bit = 0; bit < 5; ++bit)
                         if ((r >> bit) & 1) src ^= hp.ringp[TIDB + bit];
                 } else {
-                    src = hbm_gidx<TB>(l, t, c);
+                    src = hbm_gidx<TB>(l, t, c, n);
                 }
                 const unsigned slot = (unsigned)(8 * smem_swz((int)l));
                 cp_async8(psi_base + slot, gpsi + src);
@@ -216,7 +220,7 @@ hea_hbm_pass_kernel(const HeaParams<float> p, const HbmPass hp, const HbmBuffers
                     for (int bit = 0; bit < 5; ++bit)
                         if ((r >> bit) & 1) dst ^= hp.ringp[TIDB + bit];
                 } else {
-                    dst = hbm_gidx<TB>(l, t, c);
+                    dst = hbm_gidx<TB>(l, t, c, n);
                 }
                 const unsigned slot = (unsigned)(8 * smem_swz((int)l));
                 gpsi_w[dst] = lds64(psi_base + slot);
