@@ -463,9 +463,9 @@ def run_b200(args):
                     "timer": "max(CUDA events, host wall clock) over the K steps, max over ranks"},
             # this library's kernels per step: prep, circuit kernel, finalize (+ finalize_enc) — with N > 1 the
             # finalize kernel is also the all-reduce (finalize_exchange_kernel), else one peer all-reduce kernel more;
-            # the tensor-core tier adds its two operand-image prep kernels
+            # the tensor-core tier adds its two operand-image prep kernels and runs the step as forward-only + reverse-only kernels
             "gpu_launches": ((3 if getattr(trainer, "_fused_exchange", False) else
-                              (4 if trainer.fused_encoding else 3) + (1 if world > 1 else 0)) + (2 if tc_on else 0)) * K,
+                              (4 if trainer.fused_encoding else 3) + (1 if world > 1 else 0)) + (3 if tc_on else 0)) * K,
             "roofline": {"bound": "fp32", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                          "frac": achieved / peak if peak else None, "traffic": traffic,
                          "kernel": ("hea_tc_kernel<grad%s> (tcgen05 block-unitary GEMMs + FFMA2 phases / Pauli moments; +prep, finalize)"

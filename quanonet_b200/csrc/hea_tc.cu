@@ -4,21 +4,25 @@
 
 namespace qon {
 
-size_t tc_workspace_bytes(int K, int S) { return (size_t)(K + S) * kTcImgBytes + 256; }
+size_t tc_workspace_bytes(int K, int S, int64_t B) {
+    // operand images + error flag + (split training step) one 256-byte state row per sample
+    return (size_t)(K + S) * kTcImgBytes + 256 + (size_t)(B > 0 ? B : 0) * 256;
+}
 
-template <bool GRAD, bool GX, int ENC, bool DBG>
+template <bool GRAD, bool GX, int ENC, bool DBG, bool SPLIT = false>
 static cudaError_t tc_launch_t(int grid, const HeaParams<float>& p, const unsigned char* img, float* dbg, int* err,
-                               cudaStream_t st) {
+                               float* state, cudaStream_t st) {
     using G = TcGeom<GRAD>;
-    auto kern = hea_tc_kernel<GRAD, GX, ENC, DBG>;
+    auto kern = hea_tc_kernel<GRAD, GX, ENC, DBG, SPLIT>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM);
     if (e != cudaSuccess) return e;
-    kern<<<grid, G::THREADS, G::SMEM, st>>>(p, img, dbg, err);
+    kern<<<grid, G::THREADS, G::SMEM, st>>>(p, img, dbg, err, state);
     return cudaGetLastError();
 }
 
 // mode: hea_reg_inst.cuh (0 fwd | 1 grad + dL/dx | 2 grad | 3 fwd, fused encoding | 4 grad, fused encoding |
-// 5 grad, fused encoding + frequency-layer gradients).  version 1 = the first forward kernel (hea_tc.cuh), kept for A/B.
+// 5 grad, fused encoding + frequency-layer gradients).  version 1 = the first forward kernel (hea_tc.cuh), kept for A/B;
+// version 3 = the training step as one kernel (default: split into a forward-only and a reverse-only kernel).
 cudaError_t tc_launch(int mode, int version, int sms, const HeaParams<float>& p, const float* w, const DepthPack& dp,
                       char* tc_ws, float* dbg, int* err_user, cudaStream_t st) {
     unsigned char* img = reinterpret_cast<unsigned char*>(tc_ws);
@@ -33,13 +37,14 @@ cudaError_t tc_launch(int mode, int version, int sms, const HeaParams<float>& p,
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     const int64_t ntiles = (p.B + 127) / 128;
-    const int nt = grad ? 2 : 4;
-    int64_t grid = (ntiles + nt - 1) / nt;
-    if (grid > sms) grid = sms;
-    if (grid < 1) grid = 1;
-    const int g = (int)grid;
+    auto grid_for = [&](int nt) {
+        int64_t grid = (ntiles + nt - 1) / nt;
+        if (grid > sms) grid = sms;
+        return (int)(grid < 1 ? 1 : grid);
+    };
+    float* state = reinterpret_cast<float*>(tc_ws + (size_t)(p.K + p.S) * kTcImgBytes + 256);
     if (version == 1 && !grad) {
-        const int smem = kTcStages * kTcImgBytes;
+        const int smem = kTcStages * kTcImgBytes, g = grid_for(4);
         if (mode == 0) {
             auto k1 = hea_tc_fwd_kernel<0, false>;
             if ((e = cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return e;
@@ -51,15 +56,32 @@ cudaError_t tc_launch(int mode, int version, int sms, const HeaParams<float>& p,
         }
         return cudaGetLastError();
     }
+    if (!grad) {
+        const int g = grid_for(4);
+        if (mode == 0) return dbg ? tc_launch_t<false, false, 0, true>(g, p, img, dbg, err, nullptr, st)
+                                  : tc_launch_t<false, false, 0, false>(g, p, img, dbg, err, nullptr, st);
+        return tc_launch_t<false, false, 1, false>(g, p, img, dbg, err, nullptr, st);
+    }
+    const int g = grid_for(2);
+    if (version == 3 || dbg) {      // the whole step in ONE kernel (forward sweep on the gradient kernel's 2 tiles)
+        switch (mode) {
+            case 1: return dbg ? tc_launch_t<true, true, 0, true>(g, p, img, dbg, err, nullptr, st)
+                               : tc_launch_t<true, true, 0, false>(g, p, img, dbg, err, nullptr, st);
+            case 2: return tc_launch_t<true, false, 0, false>(g, p, img, dbg, err, nullptr, st);
+            case 4: return tc_launch_t<true, false, 1, false>(g, p, img, dbg, err, nullptr, st);
+            case 5: return tc_launch_t<true, false, 2, false>(g, p, img, dbg, err, nullptr, st);
+            default: return cudaErrorInvalidValue;
+        }
+    }
+    // split step: forward-only kernel (4 tiles / 16 warps) leaves the final states, the gradient kernel sweeps back
+    e = (mode == 1 || mode == 2) ? tc_launch_t<false, false, 0, false>(grid_for(4), p, img, nullptr, err, state, st)
+                                 : tc_launch_t<false, false, 1, false>(grid_for(4), p, img, nullptr, err, state, st);
+    if (e != cudaSuccess) return e;
     switch (mode) {
-        case 0: return dbg ? tc_launch_t<false, false, 0, true>(g, p, img, dbg, err, st)
-                           : tc_launch_t<false, false, 0, false>(g, p, img, dbg, err, st);
-        case 3: return tc_launch_t<false, false, 1, false>(g, p, img, dbg, err, st);
-        case 1: return dbg ? tc_launch_t<true, true, 0, true>(g, p, img, dbg, err, st)
-                           : tc_launch_t<true, true, 0, false>(g, p, img, dbg, err, st);
-        case 2: return tc_launch_t<true, false, 0, false>(g, p, img, dbg, err, st);
-        case 4: return tc_launch_t<true, false, 1, false>(g, p, img, dbg, err, st);
-        case 5: return tc_launch_t<true, false, 2, false>(g, p, img, dbg, err, st);
+        case 1: return tc_launch_t<true, true, 0, false, true>(g, p, img, nullptr, err, state, st);
+        case 2: return tc_launch_t<true, false, 0, false, true>(g, p, img, nullptr, err, state, st);
+        case 4: return tc_launch_t<true, false, 1, false, true>(g, p, img, nullptr, err, state, st);
+        case 5: return tc_launch_t<true, false, 2, false, true>(g, p, img, nullptr, err, state, st);
         default: return cudaErrorInvalidValue;
     }
 }

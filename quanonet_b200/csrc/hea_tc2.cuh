@@ -255,10 +255,14 @@ __device__ __forceinline__ bool tc_wait(uint32_t bar, uint32_t parity, int* err)
 // the kernel.  ENC as in hea_reg.cuh (0: x given, 1: fused encoding, 2: + frequency-layer gradients)
 // images: [K forward block images | S reverse sublayer images in sweep order]
 // ---------------------------------------------------------------------------------------------------------
-template <bool GRAD, bool NEED_GX, int ENC, bool DBG>
+// SPLIT: the training step as TWO kernels — the forward-only kernel (4 tiles, 16 compute warps) leaves every sample's
+// final state row in `state` (256 B per sample), the gradient kernel (SPLIT = true) starts its reverse sweep from
+// there instead of running the forward sweep itself on its 2 tiles / 8 warps.
+template <bool GRAD, bool NEED_GX, int ENC, bool DBG, bool SPLIT = false>
 __global__ void __launch_bounds__(TcGeom<GRAD>::THREADS, 1)
-hea_tc_kernel(const HeaParams<float> p, const unsigned char* __restrict__ images, float* dbg, int* err) {
+hea_tc_kernel(const HeaParams<float> p, const unsigned char* __restrict__ images, float* dbg, int* err, float* state) {
     using G = TcGeom<GRAD>;
+    static_assert(GRAD || !SPLIT, "SPLIT selects the reverse-only gradient kernel");
     constexpr int NQ = 5, NT = G::NT, NS = G::NS;
     constexpr bool FREQ_GRAD = GRAD && ENC == 2;
     constexpr bool WANT_GX = NEED_GX || FREQ_GRAD;
@@ -270,7 +274,7 @@ hea_tc_kernel(const HeaParams<float> p, const unsigned char* __restrict__ images
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t ntiles = (p.B + 127) / 128;
     const int64_t rounds = (ntiles + (int64_t)gridDim.x * NT - 1) / ((int64_t)gridDim.x * NT);
-    const int nsteps = p.K + (GRAD ? p.S : 0);
+    const int nsteps = (GRAD && SPLIT ? 0 : p.K) + (GRAD ? p.S : 0);
 
     if (threadIdx.x == 0) {
         for (int t = 0; t < NT; ++t) {
@@ -301,7 +305,7 @@ hea_tc_kernel(const HeaParams<float> p, const unsigned char* __restrict__ images
                 const int stage = (int)(g % NS);
                 const uint32_t fb = tc::smem_u32(&bar_full[t][stage]);
                 tc::mbar_expect_tx(fb, kTcImgBytes);
-                tc::bulk_g2s(ring + (uint32_t)stage * kTcImgBytes, images + (size_t)(g % nsteps) * kTcImgBytes, kTcImgBytes, fb);
+                tc::bulk_g2s(ring + (uint32_t)stage * kTcImgBytes, images + (size_t)((GRAD && SPLIT ? p.K : 0) + g % nsteps) * kTcImgBytes, kTcImgBytes, fb);
             };
             for (int64_t g = 0; g < NS - 1 && g < total; ++g) fetch(g);
             bool dead = false;
@@ -319,7 +323,7 @@ hea_tc_kernel(const HeaParams<float> p, const unsigned char* __restrict__ images
             };
             for (int64_t g = 0; g < total; ++g) {
                 const int stage = (int)(g % NS);
-                const bool rev = GRAD && (int)(g % nsteps) >= p.K;
+                const bool rev = GRAD && (SPLIT || (int)(g % nsteps) >= p.K);
                 const uint32_t sb = ring + (uint32_t)stage * kTcImgBytes;
                 if (!dead && !tc_wait(bar_a_t, apar, err)) dead = true;
                 apar ^= 1u;
@@ -396,6 +400,7 @@ hea_tc_kernel(const HeaParams<float> p, const unsigned char* __restrict__ images
 
             // ---------------------------------------------------------------- forward sweep
             float th[NQ];
+            if constexpr (!SPLIT) {
             load_angles(0, th);
             for (int k = 0; k < p.K; ++k) {
                 float thn[NQ];
@@ -442,6 +447,7 @@ hea_tc_kernel(const HeaParams<float> p, const unsigned char* __restrict__ images
                 for (int q = 0; q < NQ; ++q) th[q] = thn[q];
             }
             wait_d();
+            }
 
             if constexpr (!GRAD) {
                 // ------------------------------------------------------------ expectation value only
@@ -454,6 +460,11 @@ hea_tc_kernel(const HeaParams<float> p, const unsigned char* __restrict__ images
                     if (DBG && dump)
 #pragma unroll
                         for (int i = 0; i < 16; ++i) dbg[((size_t)(p.K - 1) * 128 + drow) * 128 + 16 * c + i] = __uint_as_float(r[i]);
+                    if (state && valid) {      // final state row for the split gradient kernel (it renormalises)
+                        uint4* dst = reinterpret_cast<uint4*>(state + b * 64 + 16 * c);
+#pragma unroll
+                        for (int v = 0; v < 4; ++v) dst[v] = make_uint4(r[4 * v], r[4 * v + 1], r[4 * v + 2], r[4 * v + 3]);
+                    }
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
                         const float re = __uint_as_float(r[2 * i]), im = __uint_as_float(r[2 * i + 1]);
@@ -470,7 +481,16 @@ hea_tc_kernel(const HeaParams<float> p, const unsigned char* __restrict__ images
             } else {
                 // ------------------------------------------------------------ expectation, lam = g H psi
                 uint32_t ps[64], lm[64];
-                tc_load_state(tDp, ps);
+                if constexpr (SPLIT) {
+                    const uint4* src = reinterpret_cast<const uint4*>(state + bc * 64);
+#pragma unroll
+                    for (int v = 0; v < 16; ++v) {
+                        const uint4 q4 = __ldcs(src + v);
+                        ps[4 * v] = q4.x; ps[4 * v + 1] = q4.y; ps[4 * v + 2] = q4.z; ps[4 * v + 3] = q4.w;
+                    }
+                } else {
+                    tc_load_state(tDp, ps);
+                }
                 if (DBG && dump)
 #pragma unroll
                     for (int i = 0; i < 64; ++i) dbg[((size_t)(p.K - 1) * 128 + drow) * 128 + i] = __uint_as_float(ps[i]);

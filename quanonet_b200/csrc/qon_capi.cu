@@ -560,7 +560,7 @@ int make_plan(int64_t B, int n, int K, const int* depth, int dtype, int mode, Pl
     if (pl->fast_hbm) off = align_up(off + pl->hp.bytes);
     else if (pl->tier == 2) off = align_up(off + (size_t)pl->grid * (grad ? 4 : 2) * ((size_t)1 << n) * es);
     pl->off_tc = off;
-    if (dtype == QON_F32 && n == 5) off = align_up(off + tc_workspace_bytes(K, (int)S));   // tensor-core tier: operand images
+    if (dtype == QON_F32 && n == 5) off = align_up(off + tc_workspace_bytes(K, (int)S, grad ? B : 0));   // tensor-core tier: operand images
     pl->total = off;
     return 0;
 }
