@@ -190,7 +190,7 @@ int qon_encoded_mse_step_dp(const void* u0, int64_t ldu0, int in0, int K0, const
  * tcgen05 tensor cores, the RX encoding layers as diagonal phases in the Hadamard basis; same results to the 1e-5
  * norm-relative bar.  On by default (QON_TC=0 in the environment disables it; QON_TC_MIN_B sets the threshold).
  *   enable     1 = on, 0 = off (the FFMA2 register kernels serve every batch), -1 = leave unchanged
- *   min_batch  smallest batch routed to the tier (default 16384); < 0 = leave unchanged
+ *   min_batch  smallest batch routed to the tier (default 12289); < 0 = leave unchanged
  *   debug_state / error_flag: device pointers for kernel bring-up (state dump of the first tile; protocol
  *   time-out flag), NULL in production — a time-out poisons the outputs with NaN, it never hangs.
  * Process-wide; returns the previous `enable`. */

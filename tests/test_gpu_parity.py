@@ -745,7 +745,7 @@ def tensor_tier_forced():
     lib = _lib.load()
     prev = tensor_tier(True, 0)
     yield
-    lib.qon_tensor_tier(int(prev), 16384, None, None)
+    lib.qon_tensor_tier(int(prev), 12289, None, None)
 
 
 def test_tensor_tier_golden_circuit_cases(cuda_device, tensor_tier_forced):
@@ -781,14 +781,14 @@ def test_tensor_tier_vs_oracle_and_register_kernels(cuda_device, depths):
     prev = tensor_tier(None)
     try:
         for tier in (True, False):
-            tensor_tier(tier, 0 if tier else 16384)
+            tensor_tier(tier, 0 if tier else 12289)
             f = hea_expval(t(x), t(w), n, depths, t(diag), 0, 0.0, 0.0, 0)
             o, gx, gw = hea_expval_backward(t(g), t(x), t(w), n, depths, t(diag), 0, 0.0, 0.0, 0, True)
             _, _, gw2 = hea_expval_backward(t(g), t(x), t(w), n, depths, t(diag), 0, 0.0, 0.0, 0, False)
             _, gxp, gwp = hea_expval_backward(t(g[:nref]), t(x[:nref]), t(w), n, depths, t(diag), 0, 0.0, 0.0, 0, True)
             res[tier] = [a.double().cpu().numpy() for a in (f[:, 0], o[:, 0], gx, gw, gw2, gxp, gwp)]
     finally:
-        _lib.load().qon_tensor_tier(int(prev), 16384, None, None)
+        _lib.load().qon_tensor_tier(int(prev), 12289, None, None)
     e_ref, gx_ref, gw_ref = orc.hea_forward_backward(x[:nref].astype(np.float64), w.astype(np.float64), n,
                                                      [(n, d) for d in depths], orc.ham_from_diag(diag, n), g[:nref].astype(np.float64))
     f, o, gx, gw, gw2, gxp, gwp = res[True]
@@ -831,13 +831,13 @@ def test_bench_config_fused_training_step_vs_oracle(cuda_device, tier):
     (b64, t64, y64), (branch, trunk, y) = _tiled_training_batch(320, 5, cuda_device)      # B = 20,480
     prev = tensor_tier(None)
     try:
-        tensor_tier(tier == "tensor", 0 if tier == "tensor" else 16384)
+        tensor_tier(tier == "tensor", 0 if tier == "tensor" else 12289)
         tr = DataParallelTrainer(model, lr=1e-3, optimizer="sgd")
         assert tr.fused_encoding
         loss = float(tr.compute_grads((branch, trunk), y))
         torch.cuda.synchronize()
     finally:
-        _lib.load().qon_tensor_tier(int(prev), 16384, None, None)
+        _lib.load().qon_tensor_tier(int(prev), 12289, None, None)
     params = {k: v.detach().double().cpu().numpy() for k, v in model.state_dict().items()}
     q = model.quantum_layer
     blocks, ham = q.block_configs, orc.ham_from_bound(n)
