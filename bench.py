@@ -448,7 +448,8 @@ def run_b200(args):
         tf = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tf):   # dram bytes per SAMPLE from the committed `ncu --set full` capture
             try:
-                key = "fused_encoding_bytes_per_sample" if trainer.fused_encoding else "x_given_bytes_per_sample"
+                key = ("tensor_tier_bytes_per_sample" if tc_on else
+                       "fused_encoding_bytes_per_sample" if trainer.fused_encoding else "x_given_bytes_per_sample")
                 traffic = json.load(open(tf))[key] * B
             except Exception:
                 traffic = None
@@ -468,7 +469,7 @@ def run_b200(args):
                               (4 if trainer.fused_encoding else 3) + (1 if world > 1 else 0)) + (3 if tc_on else 0)) * K,
             "roofline": {"bound": "fp32", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                          "frac": achieved / peak if peak else None, "traffic": traffic,
-                         "kernel": ("hea_tc_kernel<grad%s> (tcgen05 block-unitary GEMMs + FFMA2 phases / Pauli moments; +prep, finalize)"
+                         "kernel": ("hea_tc_kernel: forward-only + reverse-only gradient kernel<grad%s> (tcgen05 block-unitary GEMMs + FFMA2 phases / Pauli moments; +prep, finalize)"
                                     if tc_on else "hea_reg_kernel<float,5,0,grad%s> (+prep, finalize)") % (
                              ",fused-encoding" if trainer.fused_encoding else ""), "kernel_ms": kern_ms,
                          "flops_per_sample": f_all, "peak_source": "FFMA probe measured on this GPU in this run "
