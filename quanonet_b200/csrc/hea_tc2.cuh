@@ -55,7 +55,7 @@ __device__ __forceinline__ u64 tc_pair(const uint32_t (&r)[64], int z) {
 // ---------------------------------------------------------------------------------------------------------
 // prep of the reverse images: grid = S CTAs of 32 threads, image s' = S-1-s (execution order of the sweep).
 // Image of sublayer s (block k, sublayers s0 .. last): the COMPOSITE matrix taking the block's output cut to the cut
-// after sublayer s-1,  C_s = [H if s == s0] (R_s^+ Ring^+) ... (R_last^+ Ring^+) [H if k < K-1],
+// after sublayer s-1, in the Hadamard basis:  C_s = H (R_s^+ Ring^+) ... (R_last^+ Ring^+) [H if k < K-1],
 // so one operand split per block serves all its GEMMs.
 // ---------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(32) tc_prep_rev_kernel(const float* __restrict__ w, int K, int S, DepthPack dp,
@@ -65,7 +65,6 @@ __global__ void __launch_bounds__(32) tc_prep_rev_kernel(const float* __restrict
     const int s = blockIdx.x, j = threadIdx.x;
     int k = 0, s0 = 0;
     while (s0 + dp.d[k] <= s) { s0 += dp.d[k]; ++k; }
-    const bool first_in_block = s == s0;
     const bool input_had = k < K - 1;   // the operand is the block's OUTPUT cut, held in the Hadamard basis except for the last block
     const double h = 0.70710678118654752440;
     auto fwht = [&]() {
@@ -113,7 +112,7 @@ __global__ void __launch_bounds__(32) tc_prep_rev_kernel(const float* __restrict
             }
         }
     }
-    if (first_in_block) fwht();
+    fwht();     // EVERY cut of the reverse sweep is held in the Hadamard basis: one moment routine in the hot loop
     __half* hi = reinterpret_cast<__half*>(rimg + (size_t)(S - 1 - s) * kTcImgBytes);
     __half* lo = hi + 4096;
     auto put = [&](int nn, int kk, double v) {
@@ -553,8 +552,11 @@ hea_tc_kernel(const HeaParams<float> p, const unsigned char* __restrict__ images
                         --s;
                         // Pauli moments of sublayer s on the cut held in registers, scaled by this sample's g
                         float mv[16];
-                        if (j == d - 1 && k < p.K - 1) tc_moments<true>(ps, lm, mv);
-                        else tc_moments<false>(ps, lm, mv);
+                        // every cut is held in the Hadamard basis except the very first one (the final state, in the
+                        // computational basis): one moment routine in the steady-state loop keeps its body inside
+                        // the instruction cache (two variants: GPC instruction requests at 95 % of peak, ncu)
+                        if (k == p.K - 1 && j == d - 1) tc_moments<false>(ps, lm, mv);
+                        else tc_moments<true>(ps, lm, mv);
 #pragma unroll
                         for (int i = 0; i < 15; ++i) mv[i] *= glam;
                         const float tot = butterfly_reduce<float, 16>(mv, lane);

@@ -95,7 +95,7 @@ def expected_steps(x, w, depths, hdiag):
     s = 0
     for k, d in enumerate(depths):
         lastof[s:s + d] = s + d - 1; s += d
-    Gs = [emub.rev_matrix(w, s, lastof[s], first[s], blk[s] < K - 1) for s in range(S)]
+    Gs = [emub.rev_matrix(w, s, lastof[s], True, blk[s] < K - 1) for s in range(S)]
     steps = [[np.zeros((B, 64)), np.zeros((B, 64))] for _ in range(K + S)]
     il = lambda v: np.stack([v.real, v.imag], -1).reshape(-1)
     for b in range(B):

@@ -91,7 +91,7 @@ def tc_backward(x, w, depths, hdiag, gout):
     s = 0
     for k, d in enumerate(depths):
         lastof[s:s + d] = s + d - 1; s += d
-    Gs = [rev_matrix(w, s, lastof[s], first[s], blk[s] < K - 1) for s in range(S)]
+    Gs = [rev_matrix(w, s, lastof[s], True, blk[s] < K - 1) for s in range(S)]
     out = np.zeros(B); gx = np.zeros((B, n * K)); mom = np.zeros((S, 15))
     for b in range(B):
         amp = np.full(N, 1 / np.sqrt(N), complex)
@@ -104,7 +104,7 @@ def tc_backward(x, w, depths, hdiag, gout):
         out[b] = np.sum(hdiag * np.abs(amp) ** 2)
         psi, lam = amp, gout[b] * hdiag * amp
         for s in reversed(range(S)):
-            had = last[s] and blk[s] < K - 1
+            had = not (s == S - 1)
             if last[s]:
                 opsi, olam = psi, lam          # the block's output cut: operand of every GEMM of the block
             mom[s] += moments(psi, lam, STR["kTcStrHad"] if had else STR["kTcStrComp"])
