@@ -1,4 +1,6 @@
 // Tensor-core tier (hea_tc.cuh, hea_tc2.cuh): launch glue.
+#include <cstdlib>
+
 #include "hea_dispatch.cuh"
 #include "hea_tc2.cuh"
 
@@ -16,7 +18,8 @@ static cudaError_t tc_launch_t(int grid, const HeaParams<float>& p, const unsign
     auto kern = hea_tc_kernel<GRAD, GX, ENC, DBG, SPLIT>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM);
     if (e != cudaSuccess) return e;
-    kern<<<grid, G::THREADS, G::SMEM, st>>>(p, img, dbg, err, state);
+    static const int flags = [] { const char* e = getenv("QON_TC_FLAGS"); return e ? atoi(e) : 0; }();
+    kern<<<grid, G::THREADS, G::SMEM, st>>>(p, img, dbg, err, state, flags);
     return cudaGetLastError();
 }
 

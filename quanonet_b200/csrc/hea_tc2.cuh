@@ -259,7 +259,8 @@ __device__ __forceinline__ bool tc_wait(uint32_t bar, uint32_t parity, int* err)
 // there instead of running the forward sweep itself on its 2 tiles / 8 warps.
 template <bool GRAD, bool NEED_GX, int ENC, bool DBG, bool SPLIT = false>
 __global__ void __launch_bounds__(TcGeom<GRAD>::THREADS, 1)
-hea_tc_kernel(const HeaParams<float> p, const unsigned char* __restrict__ images, float* dbg, int* err, float* state) {
+hea_tc_kernel(const HeaParams<float> p, const unsigned char* __restrict__ images, float* dbg, int* err, float* state,
+              int flags) {
     using G = TcGeom<GRAD>;
     static_assert(GRAD || !SPLIT, "SPLIT selects the reverse-only gradient kernel");
     constexpr int NQ = 5, NT = G::NT, NS = G::NS;
@@ -539,6 +540,10 @@ hea_tc_kernel(const HeaParams<float> p, const unsigned char* __restrict__ images
                 int step = p.K;
                 load_angles(p.K - 1, th);
                 for (int k = p.K - 1; k >= 0; --k) {
+                    // flags bit 0: the two tiles of the CTA start every block together (named barrier over the 256 compute
+                    // threads), so the two warps of a scheduler run the same ~28 KB loop body at the same time and share
+                    // its instruction fetches
+                    if (flags & 1) asm volatile("bar.sync 1, %0;" ::"n"(G::COMPUTE_WARPS * 32) : "memory");
                     float thn[NQ];
                     load_angles(k > 0 ? k - 1 : 0, thn);
                     const int d = __ldg(p.depth + k);
