@@ -916,3 +916,58 @@ def test_config5_explicit_diagonals_fp64(cuda_device, diag, order):
     code = _lib.QON_DIAG_MSB0 if order == "msb0" else _lib.QON_DIAG_LSB0
     _c5_check(2, (50, 2, 50, 2), orc.ham_from_diag(diag, 2, order), (diag, code, 0.0, 0.0, _lib.QON_HAM_DIAG),
               cuda_device, seed=int(abs(sum(diag)) * 10) + len(order))
+
+
+@pytest.mark.parametrize("tf", [True, False])
+@pytest.mark.parametrize("kind", ["quanonet", "heaqnn"])
+def test_tensor_tier_fused_encoding_modes(cuda_device, tf, kind):
+    """The fused-encoding entry points on the tensor-core kernels — QuanONet and HEAQNN (no trunk source, no model
+    bias), trainable and fixed frequency layers (with / without frequency gradients), ragged batch, a non-default
+    Hamiltonian range: training-step gradients, loss and the no-grad inference path against the FFMA2 register
+    kernels on the same inputs, and the x-given kernels (unfused trainer) on the tensor tier as well."""
+    from quanonet_b200 import _lib
+    from quanonet_b200.core.models_pt import HEAQNNPT, QuanONetPT
+    from quanonet_b200.ops import tensor_tier
+    from quanonet_b200.train import DataParallelTrainer
+    dev, n, tol = cuda_device, 5, 2e-5
+    torch.manual_seed(13)
+    if kind == "quanonet":
+        mk = lambda: QuanONetPT(n, 7, 2, (3, 2, 2, 1), scale_coeff=0.3, if_trainable_freq=tf, ham_bound=(-2.0, 4.0))
+        B = 5003
+        inputs = (torch.randn(B, 7), torch.rand(B, 2))
+    else:
+        mk = lambda: HEAQNNPT(n, 6, (4, 2, 0, 0), scale_coeff=0.4, if_trainable_freq=tf)
+        B = 4500
+        inputs = (torch.randn(B, 6),)
+    y = torch.randn(B, 1)
+    m0 = mk().to(dev)
+    if tf:
+        with torch.no_grad():
+            for mod in m0.modules():
+                if hasattr(mod, "weights") and hasattr(mod, "out_features"):
+                    mod.weights.uniform_(-0.5, 0.5)
+                    mod.bias.uniform_(-3, 3)
+    ins = tuple(t.to(dev) for t in inputs)
+    yd = y.to(dev)
+    res = {}
+    prev = tensor_tier(None)
+    try:
+        for tier in (True, False):
+            tensor_tier(tier, 0 if tier else 12289)
+            for fused in (True, False):
+                m = mk().to(dev)
+                m.load_state_dict(m0.state_dict())
+                tr = DataParallelTrainer(m, lr=1e-2, optimizer="sgd", use_fused_encoding=fused)
+                loss = float(tr.compute_grads(ins, yd))
+                with torch.no_grad():
+                    pred = m(*ins)          # fused inference path (qon_encoded_forward) when `fused` models allow it
+                torch.cuda.synchronize()
+                res[(tier, fused)] = (loss, tr.flat_grad.double().cpu().numpy().copy(), pred.double().cpu().numpy())
+    finally:
+        _lib.load().qon_tensor_tier(int(prev), 12289, None, None)
+    ref = res[(False, True)]
+    for key in ((True, True), (True, False)):
+        loss, grad, pred = res[key]
+        assert abs(loss - ref[0]) <= tol * abs(ref[0]), key
+        assert rel_l2(grad, ref[1]) < tol, (key, rel_l2(grad, ref[1]))
+        assert rel_l2(pred, ref[2]) < tol, key
