@@ -971,3 +971,45 @@ def test_tensor_tier_fused_encoding_modes(cuda_device, tf, kind):
         assert abs(loss - ref[0]) <= tol * abs(ref[0]), key
         assert rel_l2(grad, ref[1]) < tol, (key, rel_l2(grad, ref[1]))
         assert rel_l2(pred, ref[2]) < tol, key
+
+
+def test_tensor_tier_cuda_graph_and_determinism(cuda_device, tensor_tier_forced):
+    """The tensor-core path keeps the C-ABI's stream contract: nothing in it synchronises the host (operand prep,
+    error-flag reset, both kernels and finalize are enqueued on the caller's stream), so a training step on it can be
+    captured and replayed, and two runs on the same inputs agree bit for bit (fixed reduction order)."""
+    from quanonet_b200.core.models_pt import QuanONetPT
+    from quanonet_b200.train import DataParallelTrainer
+    dev = cuda_device
+
+    def make():
+        torch.manual_seed(21)
+        m = QuanONetPT(5, 6, 2, (2, 2, 2, 1), scale_coeff=0.3, if_trainable_freq=True).to(dev)
+        return m, DataParallelTrainer(m, lr=1e-2, optimizer="sgd")
+    g0 = torch.Generator().manual_seed(1)
+    branch, trunk, y = (torch.randn(3001, 6, generator=g0).to(dev), torch.rand(3001, 2, generator=g0).to(dev),
+                        torch.randn(3001, 1, generator=g0).to(dev))
+    m1, t1 = make()
+    for _ in range(4):
+        l1 = t1.step((branch, trunk), y)
+    ma, ta = make()
+    for _ in range(4):
+        la = ta.step((branch, trunk), y)
+    torch.cuda.synchronize()
+    assert float(l1) == float(la)
+    for (k, a), (_, b) in zip(m1.state_dict().items(), ma.state_dict().items()):
+        assert torch.equal(a, b), k                       # bit-reproducible
+    m2, t2 = make()
+    s = torch.cuda.Stream(device=dev)
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        t2.step((branch, trunk), y)                       # step 1 eager (allocator, lazy init)
+    torch.cuda.current_stream().wait_stream(s)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        l2 = t2.step((branch, trunk), y)
+    for _ in range(3):
+        g.replay()
+    torch.cuda.synchronize()
+    for (k, a), (_, b) in zip(m1.state_dict().items(), m2.state_dict().items()):
+        assert torch.allclose(a, b, rtol=1e-5, atol=1e-6), k
+    assert abs(float(l1) - float(l2)) < 1e-5 * max(1.0, abs(float(l1)))
