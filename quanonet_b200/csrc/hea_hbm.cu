@@ -11,9 +11,18 @@ inline size_t up256(size_t v) { return (v + 255) / 256 * 256; }
 
 using PassKern = void (*)(const HeaParams<float>, const HbmPass, const HbmBuffers);
 
-PassKern pass_kernel(bool reverse, int tb) {
-    if (reverse) return tb == 13 ? hea_hbm_pass_kernel<true, 13> : hea_hbm_pass_kernel<true, 12>;
-    return tb == 13 ? hea_hbm_pass_kernel<false, 13> : hea_hbm_pass_kernel<false, 12>;
+// bulk = pass A (contiguous tiles, cp.async.bulk); QON_HBM_BULK=0 keeps the per-element gather for A/B runs
+bool bulk_enabled() {
+    static const bool v = [] { const char* e = getenv("QON_HBM_BULK"); return !(e && atoi(e) == 0); }();
+    return v;
+}
+PassKern pass_kernel(bool reverse, int tb, bool bulk) {
+    if (bulk) {
+        if (reverse) return tb == 13 ? hea_hbm_pass_kernel<true, 13, true> : hea_hbm_pass_kernel<true, 12, true>;
+        return tb == 13 ? hea_hbm_pass_kernel<false, 13, true> : hea_hbm_pass_kernel<false, 12, true>;
+    }
+    if (reverse) return tb == 13 ? hea_hbm_pass_kernel<true, 13, false> : hea_hbm_pass_kernel<true, 12, false>;
+    return tb == 13 ? hea_hbm_pass_kernel<false, 13, false> : hea_hbm_pass_kernel<false, 12, false>;
 }
 
 // tile size per direction; QON_HBM_TB_FWD / QON_HBM_TB_REV override (12 or 13) for A/B runs
@@ -64,7 +73,10 @@ void make_pass(HbmPass& hp, int n, int tb, bool passB, bool reverse) {
     for (int bit = 0; bit < kMaxTileBits; ++bit) {
         unsigned g = 0;
         if (bit < tb) g = tb == 13 ? hbm_gidx<13>(1u << bit, 0u, hp.c, n) : hbm_gidx<12>(1u << bit, 0u, hp.c, n);
-        hp.ringp[bit] = bit < tb ? hbm_ring(g, n) : 0u;
+        // plain and ring-permuted position increments; hbm_run() picks per pass (ring_load / ring_store)
+        hp.plainp[bit] = bit < tb ? hbm_pos(g) : 0u;
+        hp.ringp[bit] = bit < tb ? hbm_pos(hbm_ring(g, n)) : 0u;
+        hp.ldp[bit] = hp.stp[bit] = hp.plainp[bit];
     }
 }
 }  // namespace
@@ -86,7 +98,11 @@ HbmPlan hbm_plan(int64_t B, int n, int K, int mode) {
     pl.Sc = sc;
     pl.smem_fwd = (size_t)8 << pl.tb_fwd;              // psi tile
     pl.smem_rev = (size_t)16 << pl.tb_rev;             // psi + lam tiles
-    PassKern kf = pass_kernel(false, pl.tb_fwd), kr = pass_kernel(true, pl.tb_rev);
+    PassKern kf = pass_kernel(false, pl.tb_fwd, false), kr = pass_kernel(true, pl.tb_rev, false);
+    for (int bulk = 0; bulk < 2; ++bulk) {     // both variants of each direction need the opt-in (same footprint)
+        cudaFuncSetAttribute(pass_kernel(false, pl.tb_fwd, bulk != 0), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_fwd);
+        cudaFuncSetAttribute(pass_kernel(true, pl.tb_rev, bulk != 0), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_rev);
+    }
     if (cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_fwd) != cudaSuccess ||
         cudaFuncSetAttribute(kr, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_rev) != cudaSuccess) {
         cudaGetLastError();
@@ -127,10 +143,14 @@ cudaError_t hbm_run(const HeaParams<float>& p, const int* depth, int n, int K, i
     const int64_t N = (int64_t)1 << n;
     const int tbf = pl.tb_fwd, tbr = pl.tb_rev;
     const int thr_f = 1 << (tbf - 5), thr_r = 1 << (tbr - 5);
-    PassKern kf = pass_kernel(false, tbf), kr = pass_kernel(true, tbr);
+    const bool bulk = bulk_enabled();
+    PassKern kfA = pass_kernel(false, tbf, bulk), kfB = pass_kernel(false, tbf, false);
+    PassKern krA = pass_kernel(true, tbr, bulk), krB = pass_kernel(true, tbr, false);
     cudaError_t e;
-    if ((e = cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_fwd)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(kr, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_rev)) != cudaSuccess) return e;
+    for (PassKern k : {kfA, kfB})
+        if ((e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_fwd)) != cudaSuccess) return e;
+    for (PassKern k : {krA, krB})
+        if ((e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_rev)) != cudaSuccess) return e;
 
     HbmPass A_f, B_f, A_r, B_r;
     make_pass(A_f, n, tbf, false, false);
@@ -150,6 +170,13 @@ cudaError_t hbm_run(const HeaParams<float>& p, const int* depth, int n, int K, i
             hp.need_gx = need_gx; hp.b0 = b0; hp.nb = nb;
             return hp;
         };
+        auto route = [&](HbmPass& hp, bool ring_load, bool ring_store) {    // which position tables the pass streams through
+            hp.ring_load = ring_load; hp.ring_store = ring_store;
+            for (int bit = 0; bit < kMaxTileBits; ++bit) {
+                hp.ldp[bit] = ring_load ? hp.ringp[bit] : hp.plainp[bit];
+                hp.stp[bit] = ring_store ? hp.ringp[bit] : hp.plainp[bit];
+            }
+        };
         {
             int64_t blocks = (N * nb + 255) / 256;
             if (blocks > 4096) blocks = 4096;
@@ -159,10 +186,10 @@ cudaError_t hbm_run(const HeaParams<float>& p, const int* depth, int n, int K, i
         for (int k = 0; k < K; ++k)
             for (int j = 0; j < depth[k]; ++j, ++s) {
                 HbmPass a = fill(A_f, tbf, s, k, j);
-                kf<<<grid_for(tbf, pl.grid_fwd), thr_f, pl.smem_fwd, st>>>(p, a, hb);
+                kfA<<<grid_for(tbf, pl.grid_fwd), thr_f, pl.smem_fwd, st>>>(p, a, hb);
                 HbmPass b = fill(B_f, tbf, s, k, j);
-                b.ring_store = 1;
-                kf<<<grid_for(tbf, pl.grid_fwd), thr_f, pl.smem_fwd, st>>>(p, b, hb);
+                route(b, false, true);
+                kfB<<<grid_for(tbf, pl.grid_fwd), thr_f, pl.smem_fwd, st>>>(p, b, hb);
             }
         {
             const int64_t mt = nb << (n - kMeasureBits);
@@ -176,10 +203,10 @@ cudaError_t hbm_run(const HeaParams<float>& p, const int* depth, int n, int K, i
                 for (int j = depth[k] - 1; j >= 0; --j) {
                     --s;
                     HbmPass b = fill(B_r, tbr, s, k, j);
-                    b.ring_load = 1;
-                    kr<<<grid_for(tbr, pl.grid_rev), thr_r, pl.smem_rev, st>>>(p, b, hb);
+                    route(b, true, false);
+                    krB<<<grid_for(tbr, pl.grid_rev), thr_r, pl.smem_rev, st>>>(p, b, hb);
                     HbmPass a = fill(A_r, tbr, s, k, j);
-                    kr<<<grid_for(tbr, pl.grid_rev), thr_r, pl.smem_rev, st>>>(p, a, hb);
+                    krA<<<grid_for(tbr, pl.grid_rev), thr_r, pl.smem_rev, st>>>(p, a, hb);
                 }
             if (need_gx) {
                 int64_t blocks = (nb * n * K + 255) / 256;

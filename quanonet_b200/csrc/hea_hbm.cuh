@@ -42,7 +42,10 @@ struct HbmPass {
     int tiles_log2;               // log2(tiles per sample) = n - TB
     int need_gx;
     int64_t b0, nb;               // first sample of the chunk, samples in the chunk
-    unsigned ringp[kMaxTileBits]; // ring(gidx(e_l)) for the TB local bits
+    // HBM position of local index l = base(t) ^ XOR over the set bits b of l of tbl[b]  (GF(2)-linear: the tile
+    // index map, the CNOT-ring permutation when asked, and the storage swizzle of hbm_pos() all are)
+    unsigned ldp[kMaxTileBits], stp[kMaxTileBits];
+    unsigned plainp[kMaxTileBits], ringp[kMaxTileBits];   // host side: the two candidate tables (hbm_run copies one into ldp / stp)
 };
 
 struct HbmBuffers {
@@ -68,6 +71,11 @@ __device__ __forceinline__ void tile_store(const SmemState& st, unsigned region,
     for (int i = 0; i < 32; ++i) sts64(region + (gb ^ (unsigned)off[i]), st.a[i]);
 }
 
+// Storage order of a state in HBM: amplitude k lives at position k ^ ((k >> 5) & 31) — the shared-memory swizzle of
+// hea_smem.cuh applied to the global index (an involution touching bits 0..4 only).  A pass-A tile (2^TB contiguous
+// amplitudes) is then ALREADY in its shared-memory layout in HBM and moves with one bulk copy each way.
+__host__ __device__ __forceinline__ unsigned hbm_pos(unsigned k) { return k ^ ((k >> 5) & 31u); }
+
 __host__ __device__ __forceinline__ unsigned hbm_ring(unsigned k, int n) {
     for (int i = 0; i < n; ++i) k ^= ((k >> (i + 1 == n ? 0 : i + 1)) & 1u) << i;
     return k;
@@ -79,7 +87,9 @@ __host__ __device__ __forceinline__ unsigned hbm_gidx(unsigned l, unsigned t, in
     return (l & ((1u << c) - 1u)) | (t << c) | ((l >> c) << (c + n - TB));
 }
 
-template <bool REVERSE, int TB>
+// BULK (pass A: contiguous tiles): the tile travels with cp.async.bulk (TMA engine, one instruction per direction,
+// completion on an mbarrier / bulk group) instead of 32 eight-byte cp.async + index arithmetic per thread.
+template <bool REVERSE, int TB, bool BULK>
 __global__ void __launch_bounds__(1 << (TB - 5), REVERSE ? (TB == 13 ? 1 : 2) : (TB == 13 ? 2 : 4))
 hea_hbm_pass_kernel(const HeaParams<float> p, const HbmPass hp, const HbmBuffers hb) {
     using State = SmemState;
@@ -103,14 +113,25 @@ hea_hbm_pass_kernel(const HeaParams<float> p, const HbmPass hp, const HbmBuffers
         const int kb = ((tid >> lo) << (lo + kSmemW)) | (tid & ((1 << lo) - 1));
         return (unsigned)(8 * smem_swz(kb));
     };
-    // ring(gidx(l)) is GF(2)-linear in l = tid + THREADS * r: thread part once per tile, r part = constants
-    auto ring_base = [&](unsigned t) -> unsigned {
-        unsigned v = hbm_ring(hbm_gidx<TB>(0u, t, c, n), n);
+    // HBM position of local index l = tid + THREADS * r: tile part + thread part once per tile, r part = constants
+    auto pos_base = [&](unsigned t, bool ring, const unsigned* tbl) -> unsigned {
+        unsigned g = hbm_gidx<TB>(0u, t, c, n);
+        if (ring) g = hbm_ring(g, n);
+        unsigned v = hbm_pos(g);
 #pragma unroll
         for (int bit = 0; bit < TIDB; ++bit)
-            if ((tid >> bit) & 1) v ^= hp.ringp[bit];
+            if ((tid >> bit) & 1) v ^= tbl[bit];
         return v;
     };
+    __shared__ __align__(8) unsigned long long bulk_bar;
+    unsigned bulk_par = 0;
+    if constexpr (BULK) {
+        if (tid == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((unsigned)__cvta_generic_to_shared(&bulk_bar)) : "memory");
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+    }
 
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int64_t sl = tile >> hp.tiles_log2;            // sample slot in the chunk
@@ -123,28 +144,39 @@ hea_hbm_pass_kernel(const HeaParams<float> p, const HbmPass hp, const HbmBuffers
         const float gsample = REVERSE ? hb.gval[sl] : 1.f;
 
         // ---------------- HBM -> shared memory ----------------
-        {
-            const unsigned rbase = hp.ring_load ? ring_base(t) : 0u;
+        if constexpr (BULK) {
+            const unsigned bar = (unsigned)__cvta_generic_to_shared(&bulk_bar);
+            if (tid == 0) {
+                constexpr unsigned kBytes = 8u << TB;
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(REVERSE ? 2 * kBytes : kBytes) : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(psi_base),
+                             "l"(gpsi + ((int64_t)t << TB)), "r"(kBytes), "r"(bar) : "memory");
+                if constexpr (REVERSE)
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(lam_base),
+                                 "l"(glam + ((int64_t)t << TB)), "r"(kBytes), "r"(bar) : "memory");
+            }
+            unsigned ok = 0;
+            for (int it = 0; it < 200000 && !ok; ++it)     // bounded: ~4 s; a copy that never lands must not hang the GPU
+                asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3; selp.u32 %0, 1, 0, p; }"
+                             : "=r"(ok) : "r"(bar), "r"(bulk_par), "r"(20000u) : "memory");
+            bulk_par ^= 1u;
+        } else {
+            const unsigned rbase = pos_base(t, hp.ring_load != 0, hp.ldp);
 #pragma unroll
             for (int r = 0; r < 32; ++r) {
                 const unsigned l = (unsigned)(tid + THREADS * r);      // consecutive lanes -> consecutive amplitudes
-                unsigned src;
-                if (hp.ring_load) {
-                    src = rbase;
+                unsigned src = rbase;
 #pragma unroll
-                    for (int bit = 0; bit < 5; ++bit)
-                        if ((r >> bit) & 1) src ^= hp.ringp[TIDB + bit];
-                } else {
-                    src = hbm_gidx<TB>(l, t, c, n);
-                }
+                for (int bit = 0; bit < 5; ++bit)
+                    if ((r >> bit) & 1) src ^= hp.ldp[TIDB + bit];
                 const unsigned slot = (unsigned)(8 * smem_swz((int)l));
                 cp_async8(psi_base + slot, gpsi + src);
                 if constexpr (REVERSE) cp_async8(lam_base + slot, glam + src);
             }
             asm volatile("cp.async.commit_group;\n" ::: "memory");
             asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+            __syncthreads();
         }
-        __syncthreads();
 
         // ---------------- window passes on the tile ----------------
         const float* xk = p.x + b * p.ldx + (int64_t)hp.kblk * n;
@@ -208,26 +240,40 @@ hea_hbm_pass_kernel(const HeaParams<float> p, const HbmPass hp, const HbmBuffers
         }
 
         // ---------------- shared memory -> HBM (scatter through the ring when asked) ----------------
-        {
-            const unsigned rbase = hp.ring_store ? ring_base(t) : 0u;
+        if constexpr (BULK) {
+            // the window passes ended with a barrier; make the generic-proxy writes visible to the async proxy, then
+            // ONE bulk store per state; the tile buffer is reused only after the stores have read it
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncthreads();
+            if (tid == 0) {
+                constexpr unsigned kBytes = 8u << TB;
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gpsi_w + ((int64_t)t << TB)), "r"(psi_base),
+                             "r"(kBytes) : "memory");
+                if constexpr (REVERSE)
+                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(glam_w + ((int64_t)t << TB)),
+                                 "r"(lam_base), "r"(kBytes) : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            }
+            __syncthreads();
+        } else {
+            const unsigned rbase = pos_base(t, hp.ring_store != 0, hp.stp);
 #pragma unroll 8
             for (int r = 0; r < 32; ++r) {
                 const unsigned l = (unsigned)(tid + THREADS * r);
-                unsigned dst;
-                if (hp.ring_store) {
-                    dst = rbase;
+                unsigned dst = rbase;
 #pragma unroll
-                    for (int bit = 0; bit < 5; ++bit)
-                        if ((r >> bit) & 1) dst ^= hp.ringp[TIDB + bit];
-                } else {
-                    dst = hbm_gidx<TB>(l, t, c, n);
-                }
+                for (int bit = 0; bit < 5; ++bit)
+                    if ((r >> bit) & 1) dst ^= hp.stp[TIDB + bit];
                 const unsigned slot = (unsigned)(8 * smem_swz((int)l));
                 gpsi_w[dst] = lds64(psi_base + slot);
                 if constexpr (REVERSE) glam_w[dst] = lds64(lam_base + slot);
             }
+            __syncthreads();
         }
-        __syncthreads();
+    }
+    if constexpr (BULK) {      // the last tile's stores must complete before the CTA's shared memory goes away
+        if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
 }
 
@@ -249,15 +295,16 @@ __global__ void __launch_bounds__(256) hea_hbm_measure_kernel(const HeaParams<fl
         const u64* ps = hb.psi + sl * N;
         float e = 0.f;
         for (int i = threadIdx.x; i < (1 << kMeasureBits); i += blockDim.x) {
-            const int64_t k = t * (1 << kMeasureBits) + i;
-            const u64 v = ps[k];
+            const int64_t pos = t * (1 << kMeasureBits) + i;         // storage position; amplitude index k = hbm_pos(pos)
+            const int64_t k = (int64_t)hbm_pos((unsigned)pos);
+            const u64 v = ps[pos];
             u64 h;
             if (p.pauli == 0) {
                 h = mul2<0>(__ldg(p.hdiag + k), v);
             } else {
                 h = mul2<0>(p.offset, v);
                 for (int q = 0; q < n; ++q) {
-                    const u64 f = ps[k ^ ((int64_t)1 << q)];
+                    const u64 f = ps[hbm_pos((unsigned)(k ^ ((int64_t)1 << q)))];
                     if (p.pauli == 1) h = fma2<0>(p.coeff, f, h);
                     else h = fma2<2>(((k >> q) & 1) ? p.coeff : -p.coeff, f, h);
                 }
@@ -267,7 +314,7 @@ __global__ void __launch_bounds__(256) hea_hbm_measure_kernel(const HeaParams<fl
             unpack2(h, hr, hi);
             e = fmaf(vr, hr, e);
             e = fmaf(vi, hi, e);
-            if constexpr (GRAD) hb.lam[sl * N + k] = h;
+            if constexpr (GRAD) hb.lam[sl * N + pos] = h;
         }
 #pragma unroll
         for (int m = 16; m >= 1; m >>= 1) e += __shfl_xor_sync(0xffffffffu, e, m);
