@@ -24,8 +24,8 @@ static cudaError_t tc_launch_t(int grid, const HeaParams<float>& p, const unsign
 }
 
 // mode: hea_reg_inst.cuh (0 fwd | 1 grad + dL/dx | 2 grad | 3 fwd, fused encoding | 4 grad, fused encoding |
-// 5 grad, fused encoding + frequency-layer gradients).  version 1 = the first forward kernel (hea_tc.cuh), kept for A/B;
-// version 3 = the training step as one kernel (default: split into a forward-only and a reverse-only kernel).
+// 5 grad, fused encoding + frequency-layer gradients).  version 3 = the training step as ONE kernel, kept for A/B runs
+// (default: split into a forward-only and a reverse-only kernel).
 cudaError_t tc_launch(int mode, int version, int sms, const HeaParams<float>& p, const float* w, const DepthPack& dp,
                       char* tc_ws, float* dbg, int* err_user, cudaStream_t st) {
     unsigned char* img = reinterpret_cast<unsigned char*>(tc_ws);
@@ -46,19 +46,6 @@ cudaError_t tc_launch(int mode, int version, int sms, const HeaParams<float>& p,
         return (int)(grid < 1 ? 1 : grid);
     };
     float* state = reinterpret_cast<float*>(tc_ws + (size_t)(p.K + p.S) * kTcImgBytes + 256);
-    if (version == 1 && !grad) {
-        const int smem = kTcStages * kTcImgBytes, g = grid_for(4);
-        if (mode == 0) {
-            auto k1 = hea_tc_fwd_kernel<0, false>;
-            if ((e = cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return e;
-            k1<<<g, kTcThreads, smem, st>>>(p, img, nullptr, err);
-        } else {
-            auto k1 = hea_tc_fwd_kernel<1, false>;
-            if ((e = cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return e;
-            k1<<<g, kTcThreads, smem, st>>>(p, img, nullptr, err);
-        }
-        return cudaGetLastError();
-    }
     if (!grad) {
         const int g = grid_for(4);
         if (mode == 0) return dbg ? tc_launch_t<false, false, 0, true>(g, p, img, dbg, err, nullptr, st)

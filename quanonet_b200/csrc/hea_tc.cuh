@@ -13,13 +13,10 @@
 // accumulator: hi.hi + hi.lo + lo.hi  (the dropped lo.lo term is 2^-22 relative).  Measured parity vs the fp64
 // oracle is reported in profiles/ (same 1e-5 norm-relative bar as the FFMA2 kernels).
 //
-// Data flow per CTA (one per SM): 4 compute warpgroups, each owning one 128-sample tile whose state lives in
-// TMEM (lane = sample): D (64 f32 columns: re/im interleaved) and the A operand (64 columns: 32 of f16x2 hi,
-// 32 of f16x2 lo).  Thread = sample: tcgen05.ld its D row -> phases -> split -> tcgen05.st its A row; one elected
-// thread per warpgroup then issues the 12 MMAs of the block against the block's B image in shared memory and
-// commits to the warpgroup's mbarrier.  A 17th warp streams the B images (16 KB per block: [hi | lo], laid out
-// by the prep kernel exactly as the no-swizzle K-major shared-memory descriptor expects) through a 4-stage ring
-// with 1-D bulk async copies.  While one warpgroup waits for its MMAs the other three run their CUDA-core part.
+// This header: constants, the forward prep kernel (block matrices -> f16 hi/lo operand images) and the phase table;
+// the kernels are in hea_tc2.cuh (round 2's first forward kernel — one CTA-wide producer warp, bar.sync hand-offs —
+// measured 2.28 ms per 1M samples against 1.87 ms for the per-tile MMA warps of hea_tc2.cuh and was removed;
+// profiles/r2_tc_fwd_v1_ncu_summary.md keeps its profile).
 #pragma once
 #include "hea_common.cuh"
 #include "ffma2.cuh"
@@ -28,9 +25,7 @@
 
 namespace qon {
 
-constexpr int kTcStages = 4;
 constexpr int kTcImgBytes = 16384;             // per block: B_hi (8 KB) | B_lo (8 KB)
-constexpr int kTcThreads = 17 * 32;
 constexpr float kTcSA = 32768.f;               // state scale  (|amplitude| <= 1 -> f16 normal range)
 constexpr float kTcSB = 1.f;                   // matrix scale: 1 keeps a GEMM's output at the operand scale (lo parts of
                                                // small entries are f16 subnormals: absolute error 2^-25, norm-relative 3e-8)
@@ -170,206 +165,6 @@ __device__ __forceinline__ void tc_phase_table(const float (&th)[5], float scale
         if (z < 8) tc_cmul(xr, xi, h0r, h0i, pr[z], pi[z]);
         else tc_cmul(xr, xi, h1r, h1i, pr[z], pi[z]);
     }
-}
-
-// ---------------------------------------------------------------------------------------------------------
-// forward kernel.  ENC = 0: angles x given; 1: angles formed in-kernel from (u0, u1, fw, fb) as in hea_reg.cuh
-// ---------------------------------------------------------------------------------------------------------
-template <int ENC, bool DBG>
-__global__ void __launch_bounds__(kTcThreads, 1)
-hea_tc_fwd_kernel(const HeaParams<float> p, const unsigned char* __restrict__ bimg, float* dbg, int* err) {
-    constexpr int NQ = 5;
-    extern __shared__ __align__(1024) unsigned char tc_smem[];
-    __shared__ __align__(8) uint64_t bar_full[kTcStages], bar_empty[kTcStages], bar_d[4];
-    __shared__ uint32_t tmem_base_s;
-
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t ntiles = (p.B + 127) / 128;
-    const int64_t rounds = (ntiles + (int64_t)gridDim.x * 4 - 1) / ((int64_t)gridDim.x * 4);
-
-    if (threadIdx.x == 0) {
-        for (int i = 0; i < kTcStages; ++i) {
-            tc::mbar_init(tc::smem_u32(&bar_full[i]), 1);
-            tc::mbar_init(tc::smem_u32(&bar_empty[i]), 4);
-        }
-        for (int i = 0; i < 4; ++i) tc::mbar_init(tc::smem_u32(&bar_d[i]), 1);
-        tc::mbar_fence_init();
-    }
-    if (warp == 1) tc::tmem_alloc512(tc::smem_u32(&tmem_base_s));
-    tc::tc_fence_before();
-    __syncthreads();
-    tc::tc_fence_after();
-    const uint32_t tmem_base = tmem_base_s;
-
-    if (warp == 16) {
-        // ------------------------------------------------ B-image producer
-        if (lane == 0) {
-            const int64_t total = rounds * p.K;
-            int kblk = 0;
-            for (int64_t g = 0; g < total; ++g) {
-                const int stage = (int)(g % kTcStages);
-                if (g >= kTcStages && !tc::mbar_wait(tc::smem_u32(&bar_empty[stage]), (uint32_t)((g / kTcStages - 1) & 1), err))
-                    break;
-                tc::mbar_expect_tx(tc::smem_u32(&bar_full[stage]), kTcImgBytes);
-                tc::bulk_g2s(tc::smem_u32(tc_smem + (size_t)stage * kTcImgBytes), bimg + (size_t)kblk * kTcImgBytes,
-                             kTcImgBytes, tc::smem_u32(&bar_full[stage]));
-                if (++kblk == p.K) kblk = 0;
-            }
-        }
-        __syncwarp();
-    } else {
-        // ------------------------------------------------ compute warpgroups
-        const int wg = warp >> 2, quarter = warp & 3;
-        const uint32_t lane_sel = (uint32_t)(quarter * 32) << 16;
-        const uint32_t tD = tmem_base + lane_sel + (uint32_t)wg * 128u;   // this warp's 32 lanes of the tile
-        const uint32_t tA = tD + 64u;
-        const uint32_t mD = tmem_base + (uint32_t)wg * 128u, mA = mD + 64u;   // MMA view: all 128 lanes
-        const uint32_t bar_mine = tc::smem_u32(&bar_d[wg]);
-        const bool issuer = quarter == 0 && lane == 0;
-        constexpr uint32_t idesc = tc::idesc_f16(128, 64);
-        uint32_t dpar = 0;
-        int64_t g = 0;
-        bool dead = false;   // a wait timed out: keep the barrier protocol, skip the work
-
-        for (int64_t round = 0; round < rounds; ++round) {
-            const int64_t tile = (round * gridDim.x + blockIdx.x) * 4 + wg;
-            const int64_t b = tile * 128 + quarter * 32 + lane;
-            const bool valid = b < p.B;
-            const int64_t bc = valid ? b : p.B - 1;
-            const float* xrow = ENC == 0 ? p.x + bc * p.ldx : nullptr;
-            const float* u0row = ENC != 0 && p.u0 ? p.u0 + bc * p.ldu0 : nullptr;
-            const float* u1row = ENC != 0 ? p.u1 + bc * p.ldu1 : nullptr;
-            auto load_angles = [&](int k, float(&th)[NQ]) {
-                if constexpr (ENC == 0) {
-#pragma unroll
-                    for (int q = 0; q < NQ; ++q) th[q] = __ldg(xrow + (int64_t)k * NQ + q);
-                } else {
-                    const float* ur = k < p.K0 ? u0row : u1row;
-#pragma unroll
-                    for (int q = 0; q < NQ; ++q) {
-                        const int col = k * NQ + q;
-                        const float u = __ldg(ur + __ldg(p.uidx + col));
-                        th[q] = fmaf(u, __ldg(p.fw + col), p.fb ? __ldg(p.fb + col) : 0.f);
-                    }
-                }
-            };
-            float th[NQ];
-            load_angles(0, th);
-            for (int k = 0; k < p.K; ++k, ++g) {
-                float thn[NQ];
-                load_angles(k + 1 < p.K ? k + 1 : k, thn);
-                // phases of this block's encoding layer; the GEMM output carries sA*sB, the operand wants sA
-                float pr[16], pi[16];
-                tc_phase_table(th, k == 0 ? 1.f : 1.f / kTcSB, pr, pi);
-                if (k > 0) {
-                    if (!dead && !tc::mbar_wait(bar_mine, dpar, err)) dead = true;
-                    dpar ^= 1u;
-                    tc::tc_fence_after();
-                }
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    uint32_t r[16];
-                    if (k > 0) {
-                        tc::tmem_ld16(tD + 16u * c, r);
-                        tc::tmem_wait_ld();
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            r[2 * i] = __float_as_uint(kTcSA * 0.17677669529663688110f);
-                            r[2 * i + 1] = 0u;
-                        }
-                    }
-                    if constexpr (DBG) {
-                        if (dbg && k > 0 && blockIdx.x == 0 && wg == 0 && round == 0)
-#pragma unroll
-                            for (int i = 0; i < 16; ++i)
-                                dbg[((size_t)(k - 1) * 128 + quarter * 32 + lane) * 64 + 16 * c + i] = __uint_as_float(r[i]);
-                    }
-                    uint32_t ahi[8], alo[8];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const int z = 8 * c + i;
-                        const u64 v = pack2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
-                        u64 nv;
-                        if (z < 16) {
-                            nv = mul2<0>(pr[z], v);
-                            nv = fma2<2>(pi[z], v, nv);
-                        } else {
-                            nv = mul2<0>(pr[31 - z], v);
-                            nv = fma2<3>(pi[31 - z], v, nv);
-                        }
-                        float xr, xi;
-                        unpack2(nv, xr, xi);
-                        const float hr = __uint_as_float(__float_as_uint(xr) & 0xFFFFE000u);
-                        const float hi_ = __uint_as_float(__float_as_uint(xi) & 0xFFFFE000u);
-                        ahi[i] = tc::cvt_f16x2(hr, hi_);
-                        alo[i] = tc::cvt_f16x2(xr - hr, xi - hi_);
-                    }
-                    tc::tmem_st8(tA + 8u * c, ahi);
-                    tc::tmem_st8(tA + 32u + 8u * c, alo);
-                }
-                tc::tmem_wait_st();
-                tc::tc_fence_before();
-                asm volatile("bar.sync %0, 128;" ::"r"(1 + wg) : "memory");
-                if (issuer) {
-                    tc::tc_fence_after();
-                    const int stage = (int)(g % kTcStages);
-                    if (!dead && !tc::mbar_wait(tc::smem_u32(&bar_full[stage]), (uint32_t)((g / kTcStages) & 1), err)) dead = true;
-                    const uint32_t sb = tc::smem_u32(tc_smem + (size_t)stage * kTcImgBytes);
-                    if (!dead) {
-#pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            tc::mma_f16_ts(mD, mA + 8u * j, tc::smem_desc_kmajor(sb + 256u * j, 128u, 1024u), idesc, j > 0);
-#pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            tc::mma_f16_ts(mD, mA + 8u * j, tc::smem_desc_kmajor(sb + 8192u + 256u * j, 128u, 1024u), idesc, 1u);
-#pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            tc::mma_f16_ts(mD, mA + 32u + 8u * j, tc::smem_desc_kmajor(sb + 256u * j, 128u, 1024u), idesc, 1u);
-                    }
-                    tc::mma_commit(bar_mine);
-                    tc::mma_commit(tc::smem_u32(&bar_empty[stage]));
-                }
-#pragma unroll
-                for (int q = 0; q < NQ; ++q) th[q] = thn[q];
-            }
-            // ---------------- expectation value of the tile's final state
-            if (!dead && !tc::mbar_wait(bar_mine, dpar, err)) dead = true;
-            dpar ^= 1u;
-            tc::tc_fence_after();
-            float e = 0.f, nrm = 0.f;
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                uint32_t r[16];
-                tc::tmem_ld16(tD + 16u * c, r);
-                tc::tmem_wait_ld();
-                if constexpr (DBG) {
-                    if (dbg && blockIdx.x == 0 && wg == 0 && round == 0)
-#pragma unroll
-                        for (int i = 0; i < 16; ++i)
-                            dbg[((size_t)(p.K - 1) * 128 + quarter * 32 + lane) * 64 + 16 * c + i] = __uint_as_float(r[i]);
-                }
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const float re = __uint_as_float(r[2 * i]), im = __uint_as_float(r[2 * i + 1]);
-                    const float pz = fmaf(re, re, im * im);
-                    e = fmaf(__ldg(p.hdiag + 8 * c + i), pz, e);
-                    nrm += pz;
-                }
-            }
-            // every thread of the warpgroup has drained D before the next tile's first MMA may overwrite it:
-            // that MMA is issued after the bar.sync of the next block 0, which every thread reaches after this point
-            // The exact state has unit norm.  The tensor cores accumulate with truncation, which shrinks every
-            // amplitude by the same ~4.7e-7 per GEMM (measured: -4.76e-7 +- 0.7e-7 over 128 samples); dividing by the
-            // computed norm removes that coherent drift (5e-5 over 60 blocks -> 2e-6) and the operand scales.
-            float res = e / nrm;
-            if (__ldcg(err) != 0) res = __int_as_float(0x7fc00000);   // a barrier wait timed out: poison, never guess
-            if (valid && p.out) p.out[b] = res;
-        }
-    }
-    tc::tc_fence_before();
-    __syncthreads();
-    if (warp == 1) tc::tmem_dealloc512(tmem_base);
 }
 
 }  // namespace qon

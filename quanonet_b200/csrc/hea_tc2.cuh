@@ -7,7 +7,7 @@
 // so the registers always hold the pair (psi, lam) AFTER a sublayer's CNOT ring.  The three Pauli moments per qubit
 // that the finalize kernel turns into angle gradients are defined BEFORE the ring; CNOTs are Clifford, so they are
 // measured as Pauli strings T = Ring P_q Ring^+ (csrc/tc_strings.cuh, generated and verified by
-// scripts/gen_tc_strings.py; the whole sweep is emulated against the fp64 oracle in scripts/tc_emulate_bwd.py).
+// scripts/gen_tc_strings.py; the whole sweep is emulated against the fp64 oracle in tests/harness/tc_emulate_bwd.py).
 // The gradient of an encoding angle is a Z-type (diagonal) moment in the Hadamard basis, taken right after the
 // GEMM of a block's first sublayer, before the conjugate phases are applied.
 //

@@ -31,7 +31,7 @@ int fail(int code, const char* fmt, ...) {
 constexpr int kMaxQubits = 24;
 
 // Tensor-core tier switch (hea_tc.cuh, hea_tc2.cuh): QON_TC=0/1 in the environment, or qon_tensor_tier() at run time
-// (enable == 2 selects the first forward-only kernel of hea_tc.cuh, kept for A/B runs).
+// (enable == 3 runs the training step as one kernel instead of forward-only + reverse-only, for A/B runs).
 struct TcConfig { int enable; float* dbg; int* err; int64_t min_batch; };
 TcConfig& tc_config() {
     static TcConfig c = [] {
@@ -665,7 +665,7 @@ int run(const Job& j) {
             if constexpr (sizeof(T) == 4) {
                 int dev; DeviceInfo di;
                 if (!device_info(&dev, &di)) return fail(QON_ERR_NO_DEVICE, "no usable CUDA device");
-                e = tc_launch(mode, tcc.enable == 2 ? 1 : (tcc.enable == 3 ? 3 : 2), di.sms, (const HeaParams<float>&)p, (const float*)j.w, dp,
+                e = tc_launch(mode, tcc.enable == 3 ? 3 : 2, di.sms, (const HeaParams<float>&)p, (const float*)j.w, dp,
                               base + pl.off_tc, tcc.dbg, tcc.err, st);
             } else e = cudaErrorInvalidValue;
         } else if (pl.fast_warp) {

@@ -1,16 +1,16 @@
 """GPU check of the tensor-core tier (csrc/hea_tc.cuh): parity vs the fp64 oracle and vs the FFMA2 register
 kernel, intermediate-state dump on mismatch, and forward throughput of both at B = 1M.
-    python scripts/tc_check.py [--quick]
+    python tests/harness/tc_check.py [--quick]
 """
 import ctypes, json, os, sys, time
 import numpy as np
 import torch
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from oracle import hea_oracle as orc
 from quanonet_b200 import _lib
 from quanonet_b200.ops import hea_expval
-sys.path.insert(0, os.path.join(ROOT, "scripts"))
+sys.path.insert(0, os.path.join(ROOT, "tests", "harness"))
 import tc_emulate as emu
 
 OUT = os.path.join(ROOT, "gpurun_out")

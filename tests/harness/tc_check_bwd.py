@@ -1,14 +1,14 @@
 """GPU check of the tensor-core tier's fused forward + adjoint backward (csrc/hea_tc2.cuh): gradients vs the fp64
 oracle and vs the FFMA2 register kernel, step-by-step state dump vs the exact emulation on a small case, the fused
 encoding + MSE training step (mode 5), and timings at B = 1M.
-    python scripts/tc_check_bwd.py
+    python tests/harness/tc_check_bwd.py
 """
 import ctypes, json, os, sys
 import numpy as np
 import torch
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "scripts"))
+sys.path.insert(0, os.path.join(ROOT, "tests", "harness"))
 from oracle import hea_oracle as orc
 from quanonet_b200 import _lib
 from quanonet_b200.ops import _backward_impl, _forward_impl, encoded_mse_step

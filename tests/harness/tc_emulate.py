@@ -6,7 +6,7 @@ the f16 hi/lo split with three products (an estimate of the precision the kernel
 """
 import sys, os
 import numpy as np
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from oracle import hea_oracle as orc
 
 n, N = 5, 32

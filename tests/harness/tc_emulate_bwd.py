@@ -3,7 +3,7 @@ per-sublayer un-apply matrices, Pauli-string moments on post-ring cuts (computat
 encoding-angle gradients as Z-type moments in the Hadamard basis, finalize formulas."""
 import os, sys, re
 import numpy as np
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 from oracle import hea_oracle as orc
 import tc_emulate as emu
@@ -12,7 +12,7 @@ n, N = 5, 32
 
 
 def load_strings():
-    src = open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "quanonet_b200", "csrc", "tc_strings.cuh")).read()
+    src = open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "..", "quanonet_b200", "csrc", "tc_strings.cuh")).read()
     out = {}
     for name in ("kTcStrComp", "kTcStrHad"):
         body = src[src.index("TcString " + name):]
