@@ -627,6 +627,12 @@ hea_tc_kernel(const HeaParams<float> p, const unsigned char* __restrict__ images
 #pragma unroll
                     for (int q = 0; q < NQ; ++q) th[q] = thn[q];
                 }
+                // a barrier wait that timed out leaves garbage: poison this warp's partial sums so that the loss and
+                // every gradient of the step read NaN instead of a plausible number
+                if (lane == 0 && __ldcg(err) != 0) {
+                    atomicAdd(mrow, __int_as_float(0x7fc00000));
+                    atomicAdd(srow + 1, __int_as_float(0x7fc00000));
+                }
             }
         }
     }

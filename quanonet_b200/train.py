@@ -289,8 +289,13 @@ class DataParallelTrainer:
         if dev.type != "cuda":
             raise RuntimeError("run_host_fed needs the model on a CUDA device")
         cur = torch.cuda.current_stream(dev)
-        copy_stream = torch.cuda.Stream(device=dev)
-        slots, ready, consumed = [None, None], [torch.cuda.Event(), torch.cuda.Event()], [torch.cuda.Event(), torch.cuda.Event()]
+        hf = getattr(self, "_hf", None)
+        if hf is None:      # copy stream, events, device slots and the pinned loss landing zone live as long as the trainer
+            hf = self._hf = {"stream": torch.cuda.Stream(device=dev), "slots": [None, None],
+                             "ready": [torch.cuda.Event(), torch.cuda.Event()],
+                             "consumed": [torch.cuda.Event(), torch.cuda.Event()],
+                             "chunks": [torch.empty(1024, dtype=torch.float32).pin_memory()]}
+        copy_stream, slots, ready, consumed = hf["stream"], hf["slots"], hf["ready"], hf["consumed"]
         for c in consumed:
             c.record(cur)
         losses = []
@@ -298,7 +303,7 @@ class DataParallelTrainer:
         def enqueue(slot, inputs, y):
             with torch.cuda.stream(copy_stream):
                 copy_stream.wait_event(consumed[slot])            # the step that last read this slot is done
-                if slots[slot] is None or any(d.shape != h.shape for d, h in zip(slots[slot], (*inputs, y))):
+                if slots[slot] is None or any(d.shape != h.shape or d.dtype != h.dtype for d, h in zip(slots[slot], (*inputs, y))):
                     slots[slot] = tuple(torch.empty(h.shape, dtype=h.dtype, device=dev) for h in (*inputs, y))
                 for d, h in zip(slots[slot], (*inputs, y)):
                     d.copy_(h, non_blocking=True)
@@ -318,9 +323,9 @@ class DataParallelTrainer:
             *ins, yy = slots[slot]
             loss = self.step(tuple(ins), yy, global_batch)
             consumed[slot].record(cur)
-            if i % 1024 == 0:                                      # pinned landing zone for the losses, 4 KB at a time
-                chunk = torch.empty(1024, dtype=torch.float32).pin_memory()
-            host = chunk[i % 1024:i % 1024 + 1]
+            if i // 1024 >= len(hf["chunks"]):                     # pinned landing zone for the losses, 4 KB at a time
+                hf["chunks"].append(torch.empty(1024, dtype=torch.float32).pin_memory())
+            host = hf["chunks"][i // 1024][i % 1024:i % 1024 + 1]
             host.copy_(loss.detach().reshape(1).float(), non_blocking=True)
             losses.append(host)
             if on_loss is not None:
