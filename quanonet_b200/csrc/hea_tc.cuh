@@ -122,14 +122,14 @@ __global__ void __launch_bounds__(32) tc_prep_kernel(const float* __restrict__ w
 
 // ---------------------------------------------------------------------------------------------------------
 // phases of one encoding layer for the 16 basis states with qubit 4 = 0 (the other 16 are conjugates:
-// p[31 - z] = conj(p[z])), times `scale`:  p[z] = scale * prod_q (cos(t_q/2) -/+ i sin(t_q/2)),  - for z_q = 0
+// p[31 - z] = conj(p[z])), times `scale`:  p[z] = scale * prod_q (cos(t_q/2) -/+ i sin(t_q/2)),  - for z_q = 0;
+// kept as packed (re, im) pairs: 24 complex products of 2 FFMA2 each
 // ---------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void tc_cmul(float ar, float ai, float br, float bi, float& cr, float& ci) {
-    cr = fmaf(-ai, bi, ar * br);
-    ci = fmaf(ai, br, ar * bi);
-}
+// packed complex helpers: a (packed re, im) times the complex scalar (br, bi), or conj(a) times it — 2 FFMA2 each
+__device__ __forceinline__ u64 tc_cmul(u64 a, float br, float bi) { return fma2<2>(bi, a, mul2<0>(br, a)); }
+__device__ __forceinline__ u64 tc_cmul_conj(u64 a, float br, float bi) { return fma2<1>(bi, a, mul2<5>(br, a)); }
 
-__device__ __forceinline__ void tc_phase_table(const float (&th)[5], float scale, float (&pr)[16], float (&pi)[16]) {
+__device__ __forceinline__ void tc_phase_table(const float (&th)[5], float scale, u64 (&p)[16]) {
     float s[5], c[5];
     // five independent branch-free evaluations (one basic block: the scheduler interleaves them); the rare huge
     // angle takes the accurate slow path afterwards
@@ -140,30 +140,27 @@ __device__ __forceinline__ void tc_phase_table(const float (&th)[5], float scale
 #pragma unroll
         for (int q = 0; q < 5; ++q) sincos_half(th[q], s[q], c[q]);
     }
-    // qubits 0..2: l[z2 z1 z0]; l[7 - j] = conj(l[j])
-    float lr[4], li[4];
+    // qubits 0..2: l[z2 z1 z0] for z2 = 0; l[7 - j] = conj(l[j]).  e_q(z_q) = cos(t_q/2) -/+ i sin(t_q/2)
+    u64 l[4];
     {
-        float b0r, b0i, b1r, b1i;
-        tc_cmul(c[0], -s[0], c[1], -s[1], b0r, b0i);     // z0 = 0, z1 = 0
-        tc_cmul(c[0], s[0], c[1], -s[1], b1r, b1i);      // z0 = 1, z1 = 0
+        const u64 b0 = tc_cmul(pack2(c[0], -s[0]), c[1], -s[1]);      // z0 = 0, z1 = 0
+        const u64 b1 = tc_cmul(pack2(c[0], s[0]), c[1], -s[1]);       // z0 = 1, z1 = 0
         // z1 = 1: (z0 = 0) = conj(b1), (z0 = 1) = conj(b0)
-        tc_cmul(b0r, b0i, c[2], -s[2], lr[0], li[0]);
-        tc_cmul(b1r, b1i, c[2], -s[2], lr[1], li[1]);
-        tc_cmul(b1r, -b1i, c[2], -s[2], lr[2], li[2]);
-        tc_cmul(b0r, -b0i, c[2], -s[2], lr[3], li[3]);
+        l[0] = tc_cmul(b0, c[2], -s[2]);
+        l[1] = tc_cmul(b1, c[2], -s[2]);
+        l[2] = tc_cmul_conj(b1, c[2], -s[2]);
+        l[3] = tc_cmul_conj(b0, c[2], -s[2]);
     }
-    // qubits 3, 4 with z4 = 0: h[z3]
-    float h0r, h0i, h1r, h1i;
+    // qubits 3, 4 with z4 = 0: h[z3], carrying the scale
     const float c4 = c[4] * scale, s4 = s[4] * scale;
-    tc_cmul(c[3], -s[3], c4, -s4, h0r, h0i);
-    tc_cmul(c[3], s[3], c4, -s4, h1r, h1i);
+    float h0r, h0i, h1r, h1i;
+    unpack2(tc_cmul(pack2(c[3], -s[3]), c4, -s4), h0r, h0i);
+    unpack2(tc_cmul(pack2(c[3], s[3]), c4, -s4), h1r, h1i);
 #pragma unroll
     for (int z = 0; z < 16; ++z) {
         const int j = z & 7;
-        const float xr = j < 4 ? lr[j] : lr[7 - j];
-        const float xi = j < 4 ? li[j] : -li[7 - j];
-        if (z < 8) tc_cmul(xr, xi, h0r, h0i, pr[z], pi[z]);
-        else tc_cmul(xr, xi, h1r, h1i, pr[z], pi[z]);
+        const float hr = z < 8 ? h0r : h1r, hi = z < 8 ? h0i : h1i;
+        p[z] = j < 4 ? tc_cmul(l[j], hr, hi) : tc_cmul_conj(l[7 - j], hr, hi);
     }
 }
 

@@ -172,16 +172,16 @@ __device__ __forceinline__ void tc_store_operand(uint32_t taddr, const uint32_t 
     }
 }
 
-// r <- scale-folded phases (.) r   (CONJ: conjugate phases)
+// r <- scale-folded phases (.) r   (CONJ: conjugate phases).  v p = v_re (p_re, p_im) + v_im (-p_im, p_re): the state's
+// two components are the broadcast scalars, the packed phase is the vector operand
 template <bool CONJ>
-__device__ __forceinline__ void tc_apply_phases(uint32_t (&r)[64], const float (&pr)[16], const float (&pi)[16]) {
+__device__ __forceinline__ void tc_apply_phases(uint32_t (&r)[64], const u64 (&p)[16]) {
 #pragma unroll
     for (int z = 0; z < 32; ++z) {
-        const u64 v = tc_pair(r, z);
+        const float vr = __uint_as_float(r[2 * z]), vi = __uint_as_float(r[2 * z + 1]);
         const int t = z < 16 ? z : 31 - z;
         const bool cj = (z >= 16) != CONJ;     // p[31 - z] = conj(p[z])
-        u64 nv = mul2<0>(pr[t], v);
-        nv = cj ? fma2<3>(pi[t], v, nv) : fma2<2>(pi[t], v, nv);
+        const u64 nv = cj ? tc_cmul_conj(p[t], vr, vi) : tc_cmul(p[t], vr, vi);
         float xr, xi;
         unpack2(nv, xr, xi);
         r[2 * z] = __float_as_uint(xr);
@@ -405,8 +405,8 @@ hea_tc_kernel(const HeaParams<float> p, const unsigned char* __restrict__ images
             for (int k = 0; k < p.K; ++k) {
                 float thn[NQ];
                 load_angles(k + 1 < p.K ? k + 1 : k, thn);
-                float pr[16], pi[16];
-                tc_phase_table(th, 1.f, pr, pi);
+                u64 ph[16];
+                tc_phase_table(th, 1.f, ph);
                 if (k > 0) wait_d();
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
@@ -428,15 +428,8 @@ hea_tc_kernel(const HeaParams<float> p, const unsigned char* __restrict__ images
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
                         const int z = 8 * c + i;
-                        const u64 v = pack2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
-                        u64 nv;
-                        if (z < 16) {
-                            nv = mul2<0>(pr[z], v);
-                            nv = fma2<2>(pi[z], v, nv);
-                        } else {
-                            nv = mul2<0>(pr[31 - z], v);
-                            nv = fma2<3>(pi[31 - z], v, nv);
-                        }
+                        const float vr = __uint_as_float(r[2 * i]), vi = __uint_as_float(r[2 * i + 1]);
+                        const u64 nv = z < 16 ? tc_cmul(ph[z], vr, vi) : tc_cmul_conj(ph[31 - z], vr, vi);
                         tc_split(nv, ahi[i], alo[i]);
                     }
                     tc::tmem_st8(tAp + 8u * c, ahi);
@@ -566,8 +559,8 @@ hea_tc_kernel(const HeaParams<float> p, const unsigned char* __restrict__ images
                         for (int i = 0; i < 15; ++i) mv[i] *= glam;
                         const float tot = butterfly_reduce<float, 16>(mv, lane);
                         if ((lane & 1) == 0) atomicAdd(mrow + (int64_t)s * 16 + (lane >> 1), tot);
-                        float pr[16], pi[16];
-                        if (j == 0) tc_phase_table(th, 1.f, pr, pi);
+                        u64 ph[16];
+                        if (j == 0) tc_phase_table(th, 1.f, ph);
                         wait_d();
                         tc_load_state(tDp, ps);
                         tc_load_state(tDl, lm);
@@ -618,9 +611,9 @@ hea_tc_kernel(const HeaParams<float> p, const unsigned char* __restrict__ images
                                 }
                                 const float corr = kTcSA * rsqrtf(nr);
 #pragma unroll
-                                for (int i = 0; i < 16; ++i) { pr[i] *= corr; pi[i] *= corr; }
-                                tc_apply_phases<true>(ps, pr, pi);
-                                tc_apply_phases<true>(lm, pr, pi);
+                                for (int i = 0; i < 16; ++i) ph[i] = mul2<0>(corr, ph[i]);
+                                tc_apply_phases<true>(ps, ph);
+                                tc_apply_phases<true>(lm, ph);
                             }
                         }
                     }
