@@ -37,3 +37,12 @@ def test_world2_fused_exchange_equals_separate_allreduce_and_nccl():
 def test_world2_peer_allreduce():
     r = _torchrun("peer_allreduce_check.py", 2, 29732)
     assert r.returncode == 0, (r.stdout[-3000:], r.stderr[-3000:])
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs on one box (NVLink peer memory)")
+def test_world2_solver_cuda_graph_under_data_parallelism():
+    """B200Solver with 2 ranks: graph-replayed data-parallel steps (peer exchange + tensor lr inside the graph) equal the
+    eager loop, replicas identical, evaluate() agrees on every rank, checkpoints written by rank 0."""
+    r = _torchrun("dp_solver_graph_check.py", 2, 29733)
+    assert r.returncode == 0, (r.stdout[-3000:], r.stderr[-3000:])
+    assert "CUDA-graph replay of the data-parallel step == eager" in r.stdout

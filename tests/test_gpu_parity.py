@@ -1013,3 +1013,30 @@ def test_tensor_tier_cuda_graph_and_determinism(cuda_device, tensor_tier_forced)
     for (k, a), (_, b) in zip(m1.state_dict().items(), m2.state_dict().items()):
         assert torch.allclose(a, b, rtol=1e-5, atol=1e-6), k
     assert abs(float(l1) - float(l2)) < 1e-5 * max(1.0, abs(float(l1)))
+
+
+def test_host_fed_training_equals_device_resident(cuda_device):
+    """DataParallelTrainer.run_host_fed (double-buffered H2D from pinned memory, losses read back asynchronously) takes
+    the same steps as the device-resident loop; a model moved after the trainer was built is refused."""
+    from quanonet_b200.core.models_pt import QuanONetPT
+    from quanonet_b200.train import DataParallelTrainer
+    dev = cuda_device
+
+    def make():
+        torch.manual_seed(31)
+        m = QuanONetPT(5, 6, 2, (2, 2, 2, 1), scale_coeff=0.3, if_trainable_freq=True).to(dev)
+        return m, DataParallelTrainer(m, lr=1e-2, optimizer="sgd")
+    g0 = torch.Generator().manual_seed(2)
+    batches = [((torch.randn(257, 6, generator=g0).pin_memory(), torch.rand(257, 2, generator=g0).pin_memory()),
+                torch.randn(257, 1, generator=g0).pin_memory()) for _ in range(5)]
+    m1, t1 = make()
+    ref = [float(t1.step(tuple(a.to(dev) for a in ins), y.to(dev))) for ins, y in batches]
+    m2, t2 = make()
+    got = t2.run_host_fed(iter(batches))
+    assert got == ref
+    for (k, a), (_, b) in zip(m1.state_dict().items(), m2.state_dict().items()):
+        assert torch.equal(a, b), k
+    assert t2.run_host_fed(iter(batches[:2])) is not None          # the cached copy stream / slots are reusable
+    m2.double()
+    with pytest.raises(RuntimeError, match="no longer alias"):
+        t2.step(tuple(a.to(dev) for a in batches[0][0]), batches[0][1].to(dev))
