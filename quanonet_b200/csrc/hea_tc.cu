@@ -2,42 +2,71 @@
 #include <cstdlib>
 
 #include "hea_dispatch.cuh"
-#include "hea_tc2.cuh"
+#include "hea_tc3.cuh"
 
 namespace qon {
 
-size_t tc_workspace_bytes(int K, int S, int64_t B) {
-    // operand images + error flag + (split training step) one 256-byte state row per sample
-    return (size_t)(K + S) * kTcImgBytes + 256 + (size_t)(B > 0 ? B : 0) * 256;
+static int tc_grad_grid(int64_t B, int sms) {
+    int64_t grid = ((B + 127) / 128 + 1) / 2;
+    if (grid > sms) grid = sms;
+    return (int)(grid < 1 ? 1 : grid);
+}
+
+size_t tc_workspace_bytes(int K, int S, int64_t B, int sms) {
+    // operand images + flags (error word, max |g| bits) + (training step) one 256-byte state row per sample + the
+    // outer-product accumulators of the GEMM-form weight gradients: one per (CTA, tile slot) and block
+    return (size_t)(K + S) * kTcImgBytes + 256 +
+           (B > 0 ? (size_t)B * 256 + (size_t)2 * tc_grad_grid(B, sms) * K * kTcAccLen * sizeof(float) : 0);
+}
+
+static int tc_flags() {
+    static const int flags = [] { const char* e = getenv("QON_TC_FLAGS"); return e ? atoi(e) : 0; }();
+    return flags;
 }
 
 template <bool GRAD, bool GX, int ENC, bool DBG, bool SPLIT = false>
 static cudaError_t tc_launch_t(int grid, const HeaParams<float>& p, const unsigned char* img, float* dbg, int* err,
-                               float* state, cudaStream_t st) {
+                               float* state, cudaStream_t st, unsigned* gmax = nullptr) {
     using G = TcGeom<GRAD>;
     auto kern = hea_tc_kernel<GRAD, GX, ENC, DBG, SPLIT>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM);
     if (e != cudaSuccess) return e;
-    static const int flags = [] { const char* e = getenv("QON_TC_FLAGS"); return e ? atoi(e) : 0; }();
-    kern<<<grid, G::THREADS, G::SMEM, st>>>(p, img, dbg, err, state, flags);
+    kern<<<grid, G::THREADS, G::SMEM, st>>>(p, img, dbg, err, state, tc_flags(), gmax);
+    return cudaGetLastError();
+}
+
+template <bool GX, int ENC>
+static cudaError_t tc_launch_rev(int grid, const HeaParams<float>& p, const unsigned char* img, int* err, const float* state,
+                                 const unsigned* gmax, float* gacc, float* dbg, cudaStream_t st) {
+    auto kern = hea_tc_rev_kernel<GX, ENC>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TcRev::SMEM);
+    if (e != cudaSuccess) return e;
+    kern<<<grid, TcRev::THREADS, TcRev::SMEM, st>>>(p, img, err, state, gmax, gacc, dbg, tc_flags());
     return cudaGetLastError();
 }
 
 // mode: hea_reg_inst.cuh (0 fwd | 1 grad + dL/dx | 2 grad | 3 fwd, fused encoding | 4 grad, fused encoding |
-// 5 grad, fused encoding + frequency-layer gradients).  version 3 = the training step as ONE kernel, kept for A/B runs
-// (default: split into a forward-only and a reverse-only kernel).
+// 5 grad, fused encoding + frequency-layer gradients).  The training step, by version:
+//   4 (default)  forward-only kernel, reverse kernel with GEMM-form weight gradients (hea_tc3.cuh), moment kernel
+//   2            forward-only kernel + reverse kernel with per-sublayer Pauli-string moments (hea_tc2.cuh)
+//   3            the whole step in ONE kernel (hea_tc2.cuh)                        — 2 and 3 are kept for A/B runs
+// dbg: version 4 dumps the raw outer-product accumulator of its first tile / last block; versions 2, 3 run the
+// one-kernel step with its state dumps.
 cudaError_t tc_launch(int mode, int version, int sms, const HeaParams<float>& p, const float* w, const DepthPack& dp,
                       char* tc_ws, float* dbg, int* err_user, cudaStream_t st) {
     unsigned char* img = reinterpret_cast<unsigned char*>(tc_ws);
     const bool grad = mode == 1 || mode == 2 || mode == 4 || mode == 5;
-    int* err = err_user ? err_user : reinterpret_cast<int*>(tc_ws + (size_t)(p.K + p.S) * kTcImgBytes);
-    if (!err_user) {
-        cudaError_t e0 = cudaMemsetAsync(err, 0, sizeof(int), st);
-        if (e0 != cudaSuccess) return e0;
-    }
+    char* flag_block = tc_ws + (size_t)(p.K + p.S) * kTcImgBytes;
+    int* err = err_user ? err_user : reinterpret_cast<int*>(flag_block);
+    unsigned* gmax = reinterpret_cast<unsigned*>(flag_block + 64);
+    float* state = reinterpret_cast<float*>(flag_block + 256);
+    float* gacc = reinterpret_cast<float*>(flag_block + 256 + (size_t)(p.B > 0 ? p.B : 0) * 256);
+    const bool outer = grad && version == 4;
+    cudaError_t e = cudaMemsetAsync(flag_block, 0, 256, st);      // (a caller-provided error word is the caller's to clear)
+    if (e != cudaSuccess) return e;
     tc_prep_kernel<<<p.K, 32, 0, st>>>(w, p.K, dp, img);
-    if (grad) tc_prep_rev_kernel<<<p.S, 32, 0, st>>>(w, p.K, p.S, dp, img + (size_t)p.K * kTcImgBytes);
-    cudaError_t e = cudaGetLastError();
+    if (grad) tc_prep_rev_kernel<<<outer ? p.K : p.S, 32, 0, st>>>(w, p.K, p.S, dp, img + (size_t)p.K * kTcImgBytes, outer ? 1 : 0);
+    e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     const int64_t ntiles = (p.B + 127) / 128;
     auto grid_for = [&](int nt) {
@@ -45,7 +74,6 @@ cudaError_t tc_launch(int mode, int version, int sms, const HeaParams<float>& p,
         if (grid > sms) grid = sms;
         return (int)(grid < 1 ? 1 : grid);
     };
-    float* state = reinterpret_cast<float*>(tc_ws + (size_t)(p.K + p.S) * kTcImgBytes + 256);
     if (!grad) {
         const int g = grid_for(4);
         if (mode == 0) return dbg ? tc_launch_t<false, false, 0, true>(g, p, img, dbg, err, nullptr, st)
@@ -53,6 +81,22 @@ cudaError_t tc_launch(int mode, int version, int sms, const HeaParams<float>& p,
         return tc_launch_t<false, false, 1, false>(g, p, img, dbg, err, nullptr, st);
     }
     const int g = grid_for(2);
+    if (outer) {
+        const unsigned char* rimg = img + (size_t)p.K * kTcImgBytes;
+        e = (mode == 1 || mode == 2) ? tc_launch_t<false, false, 0, false>(grid_for(4), p, img, nullptr, err, state, st, gmax)
+                                     : tc_launch_t<false, false, 1, false>(grid_for(4), p, img, nullptr, err, state, st, gmax);
+        if (e != cudaSuccess) return e;
+        switch (mode) {
+            case 1: e = tc_launch_rev<true, 0>(g, p, rimg, err, state, gmax, gacc, dbg, st); break;
+            case 2: e = tc_launch_rev<false, 0>(g, p, rimg, err, state, gmax, gacc, dbg, st); break;
+            case 4: e = tc_launch_rev<false, 1>(g, p, rimg, err, state, gmax, gacc, dbg, st); break;
+            case 5: e = tc_launch_rev<false, 2>(g, p, rimg, err, state, gmax, gacc, dbg, st); break;
+            default: return cudaErrorInvalidValue;
+        }
+        if (e != cudaSuccess) return e;
+        tc_moment_kernel<<<p.K, 1024, 0, st>>>(gacc, 2 * g, gmax, p.hdiag, w, p.K, dp, p.mpart);
+        return cudaGetLastError();
+    }
     if (version == 3 || dbg) {      // the whole step in ONE kernel (forward sweep on the gradient kernel's 2 tiles)
         switch (mode) {
             case 1: return dbg ? tc_launch_t<true, true, 0, true>(g, p, img, dbg, err, nullptr, st)

@@ -58,13 +58,20 @@ __device__ __forceinline__ u64 tc_pair(const uint32_t (&r)[64], int z) {
 // after sublayer s-1, in the Hadamard basis:  C_s = H (R_s^+ Ring^+) ... (R_last^+ Ring^+) [H if k < K-1],
 // so one operand split per block serves all its GEMMs.
 // ---------------------------------------------------------------------------------------------------------
+// per_block (hea_tc3.cuh): grid = K CTAs, image K-1-k = the whole-block un-apply matrix C_{s0(k)} = M_k^+.
 __global__ void __launch_bounds__(32) tc_prep_rev_kernel(const float* __restrict__ w, int K, int S, DepthPack dp,
-                                                         unsigned char* __restrict__ rimg) {
+                                                         unsigned char* __restrict__ rimg, int per_block) {
     constexpr int n = 5, N = 32;
     __shared__ double vr[N][N + 1], vi[N][N + 1];
-    const int s = blockIdx.x, j = threadIdx.x;
-    int k = 0, s0 = 0;
-    while (s0 + dp.d[k] <= s) { s0 += dp.d[k]; ++k; }
+    const int j = threadIdx.x;
+    int s = blockIdx.x, k = 0, s0 = 0;
+    if (per_block) {
+        k = blockIdx.x;
+        for (int kk = 0; kk < k; ++kk) s0 += dp.d[kk];
+        s = s0;
+    } else {
+        while (s0 + dp.d[k] <= s) { s0 += dp.d[k]; ++k; }
+    }
     const bool input_had = k < K - 1;   // the operand is the block's OUTPUT cut, held in the Hadamard basis except for the last block
     const double h = 0.70710678118654752440;
     auto fwht = [&]() {
@@ -113,7 +120,7 @@ __global__ void __launch_bounds__(32) tc_prep_rev_kernel(const float* __restrict
         }
     }
     fwht();     // EVERY cut of the reverse sweep is held in the Hadamard basis: one moment routine in the hot loop
-    __half* hi = reinterpret_cast<__half*>(rimg + (size_t)(S - 1 - s) * kTcImgBytes);
+    __half* hi = reinterpret_cast<__half*>(rimg + (size_t)(per_block ? K - 1 - k : S - 1 - s) * kTcImgBytes);
     __half* lo = hi + 4096;
     auto put = [&](int nn, int kk, double v) {
         const double vs = v * (double)kTcSB;
@@ -234,6 +241,17 @@ __device__ __forceinline__ void tc_xgrad(const uint32_t (&ps)[64], const uint32_
     for (int q = 0; q < 5; ++q) gq[q] = lo2(acc[q]) + hi2(acc[q]);
 }
 
+// dL/dout of one sample: the fused MSE residual (g = gscale (out + bias - y)) or the upstream gradient
+__device__ __forceinline__ float tc_sample_g(const HeaParams<float>& p, float e, int64_t b, bool valid, float& resid) {
+    resid = 0.f;
+    if (!valid) return 0.f;
+    if (p.target) {
+        resid = e + (p.bias ? __ldg(p.bias) : 0.f) - __ldg(p.target + b);
+        return p.gscale * resid;
+    }
+    return p.gout ? __ldg(p.gout + b) : 0.f;
+}
+
 // bounded mbarrier wait without busy work: try_wait suspends in hardware for up to ~20 us per probe
 __device__ __forceinline__ bool tc_wait(uint32_t bar, uint32_t parity, int* err) {
     for (int it = 0; it < 100000; ++it) {
@@ -260,7 +278,7 @@ __device__ __forceinline__ bool tc_wait(uint32_t bar, uint32_t parity, int* err)
 template <bool GRAD, bool NEED_GX, int ENC, bool DBG, bool SPLIT = false>
 __global__ void __launch_bounds__(TcGeom<GRAD>::THREADS, 1)
 hea_tc_kernel(const HeaParams<float> p, const unsigned char* __restrict__ images, float* dbg, int* err, float* state,
-              int flags) {
+              int flags, unsigned* gmax = nullptr) {
     using G = TcGeom<GRAD>;
     static_assert(GRAD || !SPLIT, "SPLIT selects the reverse-only gradient kernel");
     constexpr int NQ = 5, NT = G::NT, NS = G::NS;
@@ -271,7 +289,7 @@ hea_tc_kernel(const HeaParams<float> p, const unsigned char* __restrict__ images
     __shared__ __align__(8) uint64_t bar_full[NT][NS], bar_a[NT], bar_d[NT];
     __shared__ uint32_t tmem_base_s;
 
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31, warp = tc::warp_uniform(threadIdx.x >> 5);
     const int64_t ntiles = (p.B + 127) / 128;
     const int64_t rounds = (ntiles + (int64_t)gridDim.x * NT - 1) / ((int64_t)gridDim.x * NT);
     const int nsteps = (GRAD && SPLIT ? 0 : p.K) + (GRAD ? p.S : 0);
@@ -288,13 +306,14 @@ hea_tc_kernel(const HeaParams<float> p, const unsigned char* __restrict__ images
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
-    const uint32_t tmem_base = tmem_base_s;
+    const uint32_t tmem_base = (uint32_t)tc::warp_uniform((int)tmem_base_s);
 
     if (warp >= G::COMPUTE_WARPS) {
-        // =================================================== MMA warps: one elected thread per tile
+        // =================================================== MMA warps: one elected thread per tile (warp-uniform warp
+        // index + elect.sync: the descriptors and TMEM addresses stay in uniform registers)
         if constexpr (GRAD) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(G::REGS_MMA));   // hand registers to the compute warps
         const int t = warp - G::COMPUTE_WARPS;
-        if (t < NT && lane == 0) {
+        if (t < NT && tc::elect_one()) {
             const uint32_t mD = tmem_base + (uint32_t)t * G::TILE_COLS;
             const uint32_t mA = mD + (GRAD ? 128u : 64u);
             const uint32_t ring = tc::smem_u32(tc_smem + (size_t)t * NS * kTcImgBytes);
@@ -471,6 +490,14 @@ hea_tc_kernel(const HeaParams<float> p, const unsigned char* __restrict__ images
                 float res = e / nrm;
                 if (__ldcg(err) != 0) res = __int_as_float(0x7fc00000);
                 if (valid && p.out) p.out[b] = res;
+                if (gmax) {
+                    // training step with GEMM-form weight gradients (hea_tc3.cuh): max |dL/dout| over the batch, as
+                    // ordered bits (non-negative floats; a NaN sorts above every number and poisons the step)
+                    float resid;
+                    const float g = tc_sample_g(p, res, b, valid, resid);
+                    const unsigned m = __reduce_max_sync(0xffffffffu, __float_as_uint(fabsf(g)));
+                    if (lane == 0) atomicMax(gmax, m);
+                }
             } else {
                 // ------------------------------------------------------------ expectation, lam = g H psi
                 uint32_t ps[64], lm[64];

@@ -560,7 +560,7 @@ int make_plan(int64_t B, int n, int K, const int* depth, int dtype, int mode, Pl
     if (pl->fast_hbm) off = align_up(off + pl->hp.bytes);
     else if (pl->tier == 2) off = align_up(off + (size_t)pl->grid * (grad ? 4 : 2) * ((size_t)1 << n) * es);
     pl->off_tc = off;
-    if (dtype == QON_F32 && n == 5) off = align_up(off + tc_workspace_bytes(K, (int)S, grad ? B : 0));   // tensor-core tier: operand images
+    if (dtype == QON_F32 && n == 5) off = align_up(off + tc_workspace_bytes(K, (int)S, grad ? B : 0, di.sms));   // tensor-core tier: operand images
     pl->total = off;
     return 0;
 }
@@ -665,7 +665,7 @@ int run(const Job& j) {
             if constexpr (sizeof(T) == 4) {
                 int dev; DeviceInfo di;
                 if (!device_info(&dev, &di)) return fail(QON_ERR_NO_DEVICE, "no usable CUDA device");
-                e = tc_launch(mode, tcc.enable == 3 ? 3 : 2, di.sms, (const HeaParams<float>&)p, (const float*)j.w, dp,
+                e = tc_launch(mode, tcc.enable == 3 ? 3 : tcc.enable == 2 ? 2 : 4, di.sms, (const HeaParams<float>&)p, (const float*)j.w, dp,
                               base + pl.off_tc, tcc.dbg, tcc.err, st);
             } else e = cudaErrorInvalidValue;
         } else if (pl.fast_warp) {

@@ -76,11 +76,32 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
         : "r"(taddr)
         : "memory");
 }
+// 16 lanes x 32 consecutive 32-bit columns (the accumulator of an M = 64 tcgen05.mma sits in lanes 0..15 of every
+// subpartition).  Fragment: thread T holds, for each group g of 8 columns, r[4g + {0,1}] = row T/4, columns
+// 8g + 2(T%4) + {0,1} and r[4g + {2,3}] = row T/4 + 8, same columns.
+__device__ __forceinline__ void tmem_ld_16x256b_x4(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.16x256b.x4.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, "
+        "[%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
 __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]),
                  "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
                  : "memory");
 }
+
+// one lane of the (converged) warp; with a warp-uniform warp index (warp_uniform) the compiler keeps the MMA thread's
+// addresses and descriptors in uniform registers instead of wrapping every tcgen05.mma in a broadcast loop
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{ .reg .pred p; elect.sync _|p, 0xffffffff; selp.u32 %0, 1, 0, p; }" : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ int warp_uniform(int v) { return __shfl_sync(0xffffffffu, v, 0); }
 
 // ---------------------------------------------------------------- descriptors
 // Instruction descriptor, kind::f16: D = f32, A = B = f16, both K-major, M x N.
@@ -89,9 +110,11 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8])
 __host__ __device__ constexpr uint32_t idesc_f16(int M, int N) {
     return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
-// Shared-memory matrix descriptor, K-major, no swizzle: core matrix = 8 rows x 16 bytes stored as 128
+// Shared-memory matrix descriptor, no swizzle.  K-major operand: core matrix = 8 rows x 16 bytes stored as 128
 // contiguous bytes; LBO = byte distance between core matrices adjacent in K, SBO = between core matrices
-// adjacent in M/N.  [0,14) addr >> 4 | [16,30) LBO >> 4 | [32,46) SBO >> 4 | [46,48) version = 1 | [61,64) swizzle = 0
+// adjacent in M/N.  MN-major operand (idesc bit 15 / 16 set): core matrix = 8 K-indices x 16 bytes (8 MN-contiguous
+// elements each); LBO = distance between groups of 8 K-indices, SBO = between groups of 8 MN-indices:
+//   offset(mn, k) = (mn & 7) * 2 + (mn >> 3) * SBO + (k & 7) * 16 + (k >> 3) * LBO  [0,14) addr >> 4 | [16,30) LBO >> 4 | [32,46) SBO >> 4 | [46,48) version = 1 | [61,64) swizzle = 0
 __device__ __forceinline__ uint64_t smem_desc_kmajor(uint32_t addr, uint32_t lbo, uint32_t sbo) {
     return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) |
            (1ull << 46);
@@ -105,6 +128,16 @@ __device__ __forceinline__ void mma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uin
         "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// D[tmem] (+)= A[smem] * B[smem]^T (both operands through shared-memory descriptors), issued by ONE thread
+__device__ __forceinline__ void mma_f16_ss(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                           uint32_t accumulate) {
+    asm volatile(
+        "{ .reg .pred p; setp.ne.b32 p, %4, 0; tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p; }" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// generic-proxy shared-memory writes (st.shared) -> visible to the async proxy (tcgen05.mma operand reads)
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 // mbarrier arrive (count 1) once every tcgen05.mma issued so far by this thread has completed
 __device__ __forceinline__ void mma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
