@@ -98,6 +98,12 @@ __device__ __forceinline__ void sincos_half(float t, float& s, float& c) {
     if (__builtin_expect(fabsf(t) > 65536.0f, 0)) { sincosf(0.5f * t, &s, &c); return; }   // Payne-Hanek territory
     sincos_half_fast(t, s, c);
 }
+// the rare huge angle, out of line: one copy of the Payne-Hanek path (with its local-memory table) per kernel
+static __device__ __noinline__ float2 sincos_half_slow(float t) {
+    float s, c;
+    sincosf(0.5f * t, &s, &c);
+    return make_float2(s, c);
+}
 __device__ __forceinline__ void sincos_half(double t, double& s, double& c) { sincos(0.5 * t, &s, &c); }
 
 // depth_per_block as a kernel parameter (constant bank: loop bounds read from it are provably warp-uniform)

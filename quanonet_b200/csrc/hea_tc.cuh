@@ -25,6 +25,19 @@
 
 namespace qon {
 
+#ifndef QON_TC_SLOW_INLINE
+#define QON_TC_SLOW_INLINE 0      // experiment switch (scripts/build_tc_variant.sh): huge-angle sin/cos inlined instead of called
+#endif
+#ifndef QON_TC_PH_LATE
+#define QON_TC_PH_LATE 1          // experiment switch: phase table of the reverse sweep after the x-gradient instead of under the GEMM wait
+#endif
+#ifndef QON_TC_UV_REUSE
+#define QON_TC_UV_REUSE 1         // experiment switch: keep the block's input values for the frequency-layer gradients (vs a second gather)
+#endif
+#ifndef QON_TC_TAB
+#define QON_TC_TAB 0              // experiment switch: frequency-layer table in shared memory (hea_tc3.cuh)
+#endif
+
 constexpr int kTcImgBytes = 16384;             // per block: B_hi (8 KB) | B_lo (8 KB)
 constexpr float kTcSA = 32768.f;               // state scale  (|amplitude| <= 1 -> f16 normal range)
 constexpr float kTcSB = 1.f;                   // matrix scale: 1 keeps a GEMM's output at the operand scale (lo parts of
@@ -138,7 +151,15 @@ __device__ __forceinline__ void tc_phase_table(const float (&th)[5], float scale
     for (int q = 0; q < 5; ++q) { sincos_half_fast(th[q], s[q], c[q]); big = fmaxf(big, fabsf(th[q])); }
     if (__builtin_expect(big > 65536.0f, 0)) {
 #pragma unroll
-        for (int q = 0; q < 5; ++q) sincos_half(th[q], s[q], c[q]);
+        for (int q = 0; q < 5; ++q) {
+#if QON_TC_SLOW_INLINE
+            sincos_half(th[q], s[q], c[q]);
+#else
+            const float2 sc = sincos_half_slow(th[q]);
+            s[q] = sc.x;
+            c[q] = sc.y;
+#endif
+        }
     }
     // qubits 0..2: l[z2 z1 z0] for z2 = 0; l[7 - j] = conj(l[j]).  e_q(z_q) = cos(t_q/2) -/+ i sin(t_q/2)
     u64 l[4];

@@ -37,7 +37,9 @@ struct TcRev {
     static constexpr int OPER_BYTES = 65536;                 // per tile: psi hi | psi lo | lam hi | lam lo, 16 KB each
     static constexpr int TILE_SMEM = OPER_BYTES + NS * kTcImgBytes;
     static constexpr int SMEM = NT * TILE_SMEM;
+    static constexpr int MAX_TABLE_K = 512;                  // frequency-layer table (index, weight, bias per angle) in shared memory
     static constexpr int REGS_COMPUTE = 232, REGS_MMA = 40;
+    static constexpr int smem_bytes(int K, bool enc) { return SMEM + (enc && K <= MAX_TABLE_K ? K * 5 * 12 : 0); }
 };
 constexpr int kTcAccLen = 2048;                              // floats per (slot, block): the 32 x 32 complex Y in fragment order
 
@@ -113,6 +115,20 @@ hea_tc_rev_kernel(const HeaParams<float> p, const unsigned char* __restrict__ im
             tc::mbar_init(tc::smem_u32(&bar_g[t]), 1);
         }
         tc::mbar_fence_init();
+    }
+    // frequency layer of the fused encoding: (input column, weight, bias) of every angle, staged once per CTA so that an
+    // angle costs ONE global load (the sample's input) instead of a chain of two
+    const bool have_tab = QON_TC_TAB && ENC != 0 && p.K <= G::MAX_TABLE_K;
+    int* tab_idx = reinterpret_cast<int*>(tc_smem + G::SMEM);
+    float* tab_fw = reinterpret_cast<float*>(tab_idx + p.K * NQ);
+    float* tab_fb = tab_fw + p.K * NQ;
+    if constexpr (ENC != 0) {
+        if (have_tab)
+            for (int i = threadIdx.x; i < p.K * NQ; i += G::THREADS) {
+                tab_idx[i] = __ldg(p.uidx + i);
+                tab_fw[i] = __ldg(p.fw + i);
+                tab_fb[i] = p.fb ? __ldg(p.fb + i) : 0.f;
+            }
     }
     if (warp == G::COMPUTE_WARPS) tc::tmem_alloc512(tc::smem_u32(&tmem_base_s));
     tc::tc_fence_before();
@@ -241,7 +257,8 @@ hea_tc_rev_kernel(const HeaParams<float> p, const unsigned char* __restrict__ im
             const float* xrow = ENC == 0 ? p.x + bc * p.ldx : nullptr;
             const float* u0row = ENC != 0 && p.u0 ? p.u0 + bc * p.ldu0 : nullptr;
             const float* u1row = ENC != 0 ? p.u1 + bc * p.ldu1 : nullptr;
-            auto load_angles = [&](int k, float(&th)[NQ]) {
+            // angles of block k; uv: the sample's inputs behind them (kept for the frequency-layer gradients of the block)
+            auto load_angles = [&](int k, float(&th)[NQ], float(&uv)[FREQ_GRAD && QON_TC_UV_REUSE ? NQ : 1]) {
                 if constexpr (ENC == 0) {
 #pragma unroll
                     for (int q = 0; q < NQ; ++q) th[q] = __ldg(xrow + (int64_t)k * NQ + q);
@@ -250,8 +267,9 @@ hea_tc_rev_kernel(const HeaParams<float> p, const unsigned char* __restrict__ im
 #pragma unroll
                     for (int q = 0; q < NQ; ++q) {
                         const int col = k * NQ + q;
-                        const float u = __ldg(ur + __ldg(p.uidx + col));
-                        th[q] = fmaf(u, __ldg(p.fw + col), p.fb ? __ldg(p.fb + col) : 0.f);
+                        const float u = __ldg(ur + (have_tab ? tab_idx[col] : __ldg(p.uidx + col)));
+                        th[q] = fmaf(u, have_tab ? tab_fw[col] : __ldg(p.fw + col), have_tab ? tab_fb[col] : (p.fb ? __ldg(p.fb + col) : 0.f));
+                        if constexpr (FREQ_GRAD && QON_TC_UV_REUSE) uv[q] = u;
                     }
                 }
             };
@@ -302,24 +320,31 @@ hea_tc_rev_kernel(const HeaParams<float> p, const unsigned char* __restrict__ im
 
             // ------------------------------------------------------------ reverse (adjoint) sweep, one step per block
             float* gxrow = NEED_GX ? p.gx + (valid ? b : 0) * p.ldgx : nullptr;
-            float th[NQ];
-            load_angles(p.K - 1, th);
+            float th[NQ], uv[FREQ_GRAD && QON_TC_UV_REUSE ? NQ : 1];
+            load_angles(p.K - 1, th, uv);
             for (int k = p.K - 1; k >= 0; --k) {
-                float thn[NQ];
-                load_angles(k > 0 ? k - 1 : 0, thn);
+                float thn[NQ], uvn[FREQ_GRAD && QON_TC_UV_REUSE ? NQ : 1];
+                load_angles(k > 0 ? k - 1 : 0, thn, uvn);
                 // (ps, lm) = the block's output cut: one split feeds the un-apply GEMMs and the outer product
                 tc_store_operand2<false>(tAp, op, op + 16384, ps);
                 tc_store_operand2<true>(tAl, op + 32768, op + 49152, lm);
                 signal_a();
-                // this slot's running sums of block k: fetched now (L2 / HBM latency), added when the outer product is done
+                // this slot's running sums of block k (written a whole round ago): loaded now, added when the outer product
+                // is drained; those of block k-1 are pulled towards L2 meanwhile
                 float4* ak = reinterpret_cast<float4*>(acc + ((size_t)(blockIdx.x * NT + t) * p.K + k) * kTcAccLen) + quarter * 128 + lane;
                 float4 old4[4];
                 if (round > 0) {
 #pragma unroll
                     for (int v = 0; v < 4; ++v) old4[v] = __ldcg(ak + 32 * v);
+                    if (k > 0 && (lane & 7) == 0) {
+#pragma unroll
+                        for (int v = 0; v < 4; ++v) asm volatile("prefetch.global.L2 [%0];" ::"l"(ak - kTcAccLen / 4 + 32 * v));
+                    }
                 }
                 u64 ph[16];
+#if !QON_TC_PH_LATE
                 tc_phase_table(th, 1.f, ph);
+#endif
                 wait_on(bar_d_t, dpar);
                 tc_load_state(tDp, ps);
                 tc_load_state(tDl, lm);
@@ -340,8 +365,11 @@ hea_tc_rev_kernel(const HeaParams<float> p, const unsigned char* __restrict__ im
                         }
                         if constexpr (FREQ_GRAD) {
                             const int col = k * NQ + q;
-                            const float uval = __ldg((k < p.K0 ? u0row : u1row) + __ldg(p.uidx + col));
-                            fv[2 * q] = gxv * uval;
+#if QON_TC_UV_REUSE
+                            fv[2 * q] = gxv * uv[q];
+#else
+                            fv[2 * q] = gxv * __ldg((k < p.K0 ? u0row : u1row) + __ldg(p.uidx + col));
+#endif
                             fv[2 * q + 1] = gxv;
                         }
                     }
@@ -351,15 +379,18 @@ hea_tc_rev_kernel(const HeaParams<float> p, const unsigned char* __restrict__ im
                     }
                 }
                 if (k > 0) {
+#if QON_TC_PH_LATE
+                    tc_phase_table(th, 1.f, ph);
+#endif
                     // conjugate phases; the scale restores |psi| = sA (the truncating accumulation shrinks both states
                     // by the same factor per GEMM), applied to lam as well
-                    float nr = 0.f;
+                    float nr4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
                     for (int z = 0; z < 32; ++z) {
                         const float re = __uint_as_float(ps[2 * z]), im = __uint_as_float(ps[2 * z + 1]);
-                        nr += fmaf(re, re, im * im);
+                        nr4[z & 3] = fmaf(re, re, fmaf(im, im, nr4[z & 3]));
                     }
-                    const float corr = kTcSA * rsqrtf(nr);
+                    const float corr = kTcSA * rsqrtf((nr4[0] + nr4[1]) + (nr4[2] + nr4[3]));
 #pragma unroll
                     for (int i = 0; i < 16; ++i) ph[i] = mul2<0>(corr, ph[i]);
                     tc_apply_phases<true>(ps, ph);
@@ -394,7 +425,10 @@ hea_tc_rev_kernel(const HeaParams<float> p, const unsigned char* __restrict__ im
                     }
                 }
 #pragma unroll
-                for (int q = 0; q < NQ; ++q) th[q] = thn[q];
+                for (int q = 0; q < NQ; ++q) {
+                    th[q] = thn[q];
+                    if constexpr (FREQ_GRAD && QON_TC_UV_REUSE) uv[q] = uvn[q];
+                }
             }
             // a barrier wait that timed out leaves garbage: poison this warp's partial sums so that the loss and
             // every gradient of the step read NaN instead of a plausible number
