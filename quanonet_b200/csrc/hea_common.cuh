@@ -54,6 +54,8 @@ struct HeaParams {
     const int* uidx;     // (n*K,) source-row index of every column (prep kernel: local column % in)
     const T* fw;         // (n*K,) frequency weights (fixed-scale mode: the constant scale)
     const T* fb;         // (n*K,) frequency bias, or null
+    int in0, in1;        // input widths of the two sources (uidx[c] = local column % in): kernels that want the index
+                         // without a dependent load recompute it
 };
 
 // slots per block for the frequency-layer gradients: (d/dfw, d/dfb) per qubit, padded for the butterfly

@@ -39,10 +39,9 @@ template <bool GX, int ENC>
 static cudaError_t tc_launch_rev(int grid, const HeaParams<float>& p, const unsigned char* img, int* err, const float* state,
                                  const unsigned* gmax, float* gacc, float* dbg, cudaStream_t st) {
     auto kern = hea_tc_rev_kernel<GX, ENC>;
-    const int smem = TcRev::smem_bytes(p.K, ENC != 0);
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TcRev::SMEM);
     if (e != cudaSuccess) return e;
-    kern<<<grid, TcRev::THREADS, smem, st>>>(p, img, err, state, gmax, gacc, dbg, tc_flags());
+    kern<<<grid, TcRev::THREADS, TcRev::SMEM, st>>>(p, img, err, state, gmax, gacc, dbg, tc_flags());
     return cudaGetLastError();
 }
 

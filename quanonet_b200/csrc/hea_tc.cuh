@@ -28,16 +28,6 @@ namespace qon {
 #ifndef QON_TC_SLOW_INLINE
 #define QON_TC_SLOW_INLINE 0      // experiment switch (scripts/build_tc_variant.sh): huge-angle sin/cos inlined instead of called
 #endif
-#ifndef QON_TC_PH_LATE
-#define QON_TC_PH_LATE 1          // experiment switch: phase table of the reverse sweep after the x-gradient instead of under the GEMM wait
-#endif
-#ifndef QON_TC_UV_REUSE
-#define QON_TC_UV_REUSE 1         // experiment switch: keep the block's input values for the frequency-layer gradients (vs a second gather)
-#endif
-#ifndef QON_TC_TAB
-#define QON_TC_TAB 0              // experiment switch: frequency-layer table in shared memory (hea_tc3.cuh)
-#endif
-
 constexpr int kTcImgBytes = 16384;             // per block: B_hi (8 KB) | B_lo (8 KB)
 constexpr float kTcSA = 32768.f;               // state scale  (|amplitude| <= 1 -> f16 normal range)
 constexpr float kTcSB = 1.f;                   // matrix scale: 1 keeps a GEMM's output at the operand scale (lo parts of

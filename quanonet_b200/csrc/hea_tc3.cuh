@@ -37,9 +37,7 @@ struct TcRev {
     static constexpr int OPER_BYTES = 65536;                 // per tile: psi hi | psi lo | lam hi | lam lo, 16 KB each
     static constexpr int TILE_SMEM = OPER_BYTES + NS * kTcImgBytes;
     static constexpr int SMEM = NT * TILE_SMEM;
-    static constexpr int MAX_TABLE_K = 512;                  // frequency-layer table (index, weight, bias per angle) in shared memory
     static constexpr int REGS_COMPUTE = 232, REGS_MMA = 40;
-    static constexpr int smem_bytes(int K, bool enc) { return SMEM + (enc && K <= MAX_TABLE_K ? K * 5 * 12 : 0); }
 };
 constexpr int kTcAccLen = 2048;                              // floats per (slot, block): the 32 x 32 complex Y in fragment order
 
@@ -99,7 +97,7 @@ hea_tc_rev_kernel(const HeaParams<float> p, const unsigned char* __restrict__ im
     constexpr bool WANT_GX = NEED_GX || FREQ_GRAD;
     static_assert(!(NEED_GX && ENC != 0), "grad_x is only materialised when x is");
     extern __shared__ __align__(1024) unsigned char tc_smem[];
-    __shared__ __align__(8) uint64_t bar_full[NT][NS], bar_a[NT], bar_x[NT], bar_d[NT], bar_g[NT];
+    __shared__ __align__(8) uint64_t bar_full[NT][NS], bar_a[NT], bar_a2[NT], bar_x[NT], bar_d[NT], bar_g[NT];
     __shared__ uint32_t tmem_base_s;
 
     const int lane = threadIdx.x & 31, warp = tc::warp_uniform(threadIdx.x >> 5);
@@ -110,25 +108,12 @@ hea_tc_rev_kernel(const HeaParams<float> p, const unsigned char* __restrict__ im
         for (int t = 0; t < NT; ++t) {
             for (int i = 0; i < NS; ++i) tc::mbar_init(tc::smem_u32(&bar_full[t][i]), 1);
             tc::mbar_init(tc::smem_u32(&bar_a[t]), 4);
+            tc::mbar_init(tc::smem_u32(&bar_a2[t]), 4);
             tc::mbar_init(tc::smem_u32(&bar_x[t]), 1);
             tc::mbar_init(tc::smem_u32(&bar_d[t]), 1);
             tc::mbar_init(tc::smem_u32(&bar_g[t]), 1);
         }
         tc::mbar_fence_init();
-    }
-    // frequency layer of the fused encoding: (input column, weight, bias) of every angle, staged once per CTA so that an
-    // angle costs ONE global load (the sample's input) instead of a chain of two
-    const bool have_tab = QON_TC_TAB && ENC != 0 && p.K <= G::MAX_TABLE_K;
-    int* tab_idx = reinterpret_cast<int*>(tc_smem + G::SMEM);
-    float* tab_fw = reinterpret_cast<float*>(tab_idx + p.K * NQ);
-    float* tab_fb = tab_fw + p.K * NQ;
-    if constexpr (ENC != 0) {
-        if (have_tab)
-            for (int i = threadIdx.x; i < p.K * NQ; i += G::THREADS) {
-                tab_idx[i] = __ldg(p.uidx + i);
-                tab_fw[i] = __ldg(p.fw + i);
-                tab_fb[i] = p.fb ? __ldg(p.fb + i) : 0.f;
-            }
     }
     if (warp == G::COMPUTE_WARPS) tc::tmem_alloc512(tc::smem_u32(&tmem_base_s));
     tc::tc_fence_before();
@@ -146,7 +131,7 @@ hea_tc_rev_kernel(const HeaParams<float> p, const unsigned char* __restrict__ im
             const uint32_t mG = mA;                                        // outer-product accumulator: aliases A psi
             const uint32_t oper = tc::smem_u32(tc_smem + (size_t)t * G::TILE_SMEM);
             const uint32_t ring = oper + G::OPER_BYTES;
-            const uint32_t bar_a_t = tc::smem_u32(&bar_a[t]), bar_x_t = tc::smem_u32(&bar_x[t]);
+            const uint32_t bar_a_t = tc::smem_u32(&bar_a[t]), bar_a2_t = tc::smem_u32(&bar_a2[t]), bar_x_t = tc::smem_u32(&bar_x[t]);
             const uint32_t bar_d_t = tc::smem_u32(&bar_d[t]), bar_g_t = tc::smem_u32(&bar_g[t]);
             constexpr uint32_t idesc = tc::idesc_f16(128, 64);
             constexpr uint32_t idesc_o = tc::idesc_f16(64, 64) | (1u << 15) | (1u << 16);      // A, B MN-major
@@ -194,8 +179,10 @@ hea_tc_rev_kernel(const HeaParams<float> p, const unsigned char* __restrict__ im
                 apar ^= 1u;
                 tc::tc_fence_after();
                 if (!dead && !tc_wait(tc::smem_u32(&bar_full[t][stage]), (uint32_t)((g / NS) & 1), err)) dead = true;
-                if (!dead) gemm(mD, mA, sb);
+                if (!dead) gemm(mD, mA, sb);                       // psi: runs while the compute warps still split lam
                 tc::mma_commit(bar_x_t);
+                if (!dead && !tc_wait(bar_a2_t, apar ^ 1u, err)) dead = true;
+                tc::tc_fence_after();
                 if (!dead) gemm(mD + 64u, mA + 64u, sb);
                 tc::mma_commit(bar_d_t);
                 // the A psi columns are free once the psi GEMM has completed (the lam GEMM keeps the pipe busy meanwhile)
@@ -219,7 +206,8 @@ hea_tc_rev_kernel(const HeaParams<float> p, const unsigned char* __restrict__ im
         const uint32_t tAl = tAp + 64u;                                              // A lam
         const int srow_t = quarter * 32 + lane;                                      // sample row inside the tile
         unsigned char* op = tc_smem + (size_t)t * G::TILE_SMEM + (srow_t >> 3) * 1024 + (srow_t & 7) * 16;
-        const uint32_t bar_a_t = tc::smem_u32(&bar_a[t]), bar_d_t = tc::smem_u32(&bar_d[t]), bar_g_t = tc::smem_u32(&bar_g[t]);
+        const uint32_t bar_a_t = tc::smem_u32(&bar_a[t]), bar_a2_t = tc::smem_u32(&bar_a2[t]);
+        const uint32_t bar_d_t = tc::smem_u32(&bar_d[t]), bar_g_t = tc::smem_u32(&bar_g[t]);
         uint32_t dpar = 0, gpar = 0;
         bool dead = false;
         auto wait_on = [&](uint32_t bar, uint32_t& par) {
@@ -227,12 +215,12 @@ hea_tc_rev_kernel(const HeaParams<float> p, const unsigned char* __restrict__ im
             par ^= 1u;
             tc::tc_fence_after();
         };
-        auto signal_a = [&]() {      // "operands written": the MMA warp may issue the block's GEMMs
+        auto signal = [&](uint32_t bar) {      // "operand written": the MMA warp may issue the GEMMs that read it
             tc::fence_proxy_async_smem();
             tc::tmem_wait_st();
             tc::tc_fence_before();
             __syncwarp();
-            if (lane == 0) tc::mbar_arrive(bar_a_t);
+            if (lane == 0) tc::mbar_arrive(bar);
         };
         float hmax = 1.f;
         {
@@ -248,6 +236,13 @@ hea_tc_rev_kernel(const HeaParams<float> p, const unsigned char* __restrict__ im
         float* frow = mrow + (int64_t)p.S * 16;
         float* srow = frow + (int64_t)p.K * 16;
 
+        int qm0[NQ], qm1[NQ];        // q % in of the two input sources
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+            qm0[q] = ENC != 0 ? q % p.in0 : 0;
+            qm1[q] = ENC != 0 ? q % p.in1 : 0;
+        }
+
         for (int64_t round = 0; round < rounds; ++round) {
             const int64_t tile = (round * gridDim.x + blockIdx.x) * NT + t;
             const int64_t b = tile * 128 + quarter * 32 + lane;
@@ -257,20 +252,33 @@ hea_tc_rev_kernel(const HeaParams<float> p, const unsigned char* __restrict__ im
             const float* xrow = ENC == 0 ? p.x + bc * p.ldx : nullptr;
             const float* u0row = ENC != 0 && p.u0 ? p.u0 + bc * p.ldu0 : nullptr;
             const float* u1row = ENC != 0 ? p.u1 + bc * p.ldu1 : nullptr;
-            // angles of block k; uv: the sample's inputs behind them (kept for the frequency-layer gradients of the block)
-            auto load_angles = [&](int k, float(&th)[NQ], float(&uv)[FREQ_GRAD && QON_TC_UV_REUSE ? NQ : 1]) {
+            // The angles of block k are loaded ONE BLOCK AHEAD as raw inputs (un) and turned into angles at the bottom of
+            // the iteration, when the gather has long arrived: an in-order warp stalls at the first use of a load, and with
+            // two warps per scheduler nobody covers for it.  The input column of angle c is uidx[c] = local column % in
+            // (prep kernel, qon_capi.cu); it is recomputed from the block index here, so the gather does not hang on a
+            // load of the index table.
+            auto load_inputs = [&](int k, float(&un)[NQ]) {
                 if constexpr (ENC == 0) {
 #pragma unroll
-                    for (int q = 0; q < NQ; ++q) th[q] = __ldg(xrow + (int64_t)k * NQ + q);
+                    for (int q = 0; q < NQ; ++q) un[q] = __ldg(xrow + (int64_t)k * NQ + q);
                 } else {
-                    const float* ur = k < p.K0 ? u0row : u1row;
+                    const bool s0 = k < p.K0;
+                    const float* ur = s0 ? u0row : u1row;
+                    const int in = s0 ? p.in0 : p.in1;
+                    const int base = ((s0 ? k : k - p.K0) * NQ) % in;
 #pragma unroll
                     for (int q = 0; q < NQ; ++q) {
-                        const int col = k * NQ + q;
-                        const float u = __ldg(ur + (have_tab ? tab_idx[col] : __ldg(p.uidx + col)));
-                        th[q] = fmaf(u, have_tab ? tab_fw[col] : __ldg(p.fw + col), have_tab ? tab_fb[col] : (p.fb ? __ldg(p.fb + col) : 0.f));
-                        if constexpr (FREQ_GRAD && QON_TC_UV_REUSE) uv[q] = u;
+                        int idx = base + (s0 ? qm0[q] : qm1[q]);
+                        if (idx >= in) idx -= in;
+                        un[q] = __ldg(ur + idx);
                     }
+                }
+            };
+            auto angles_from = [&](int k, const float(&un)[NQ], float(&th)[NQ]) {
+#pragma unroll
+                for (int q = 0; q < NQ; ++q) {
+                    if constexpr (ENC == 0) th[q] = un[q];
+                    else th[q] = fmaf(un[q], __ldg(p.fw + k * NQ + q), p.fb ? __ldg(p.fb + k * NQ + q) : 0.f);
                 }
             };
 
@@ -320,31 +328,25 @@ hea_tc_rev_kernel(const HeaParams<float> p, const unsigned char* __restrict__ im
 
             // ------------------------------------------------------------ reverse (adjoint) sweep, one step per block
             float* gxrow = NEED_GX ? p.gx + (valid ? b : 0) * p.ldgx : nullptr;
-            float th[NQ], uv[FREQ_GRAD && QON_TC_UV_REUSE ? NQ : 1];
-            load_angles(p.K - 1, th, uv);
+            float th[NQ], uv[NQ];        // uv: the inputs behind th (frequency-layer gradients)
+            load_inputs(p.K - 1, uv);
+            angles_from(p.K - 1, uv, th);
             for (int k = p.K - 1; k >= 0; --k) {
-                float thn[NQ], uvn[FREQ_GRAD && QON_TC_UV_REUSE ? NQ : 1];
-                load_angles(k > 0 ? k - 1 : 0, thn, uvn);
+                float un[NQ];
+                load_inputs(k > 0 ? k - 1 : 0, un);
                 // (ps, lm) = the block's output cut: one split feeds the un-apply GEMMs and the outer product
                 tc_store_operand2<false>(tAp, op, op + 16384, ps);
+                signal(bar_a_t);
                 tc_store_operand2<true>(tAl, op + 32768, op + 49152, lm);
-                signal_a();
+                signal(bar_a2_t);
                 // this slot's running sums of block k (written a whole round ago): loaded now, added when the outer product
-                // is drained; those of block k-1 are pulled towards L2 meanwhile
+                // is drained (an L2 prefetch of block k-1's at this point measured 4 % SLOWER: 8.93 vs 8.56 ms per step)
                 float4* ak = reinterpret_cast<float4*>(acc + ((size_t)(blockIdx.x * NT + t) * p.K + k) * kTcAccLen) + quarter * 128 + lane;
                 float4 old4[4];
                 if (round > 0) {
 #pragma unroll
                     for (int v = 0; v < 4; ++v) old4[v] = __ldcg(ak + 32 * v);
-                    if (k > 0 && (lane & 7) == 0) {
-#pragma unroll
-                        for (int v = 0; v < 4; ++v) asm volatile("prefetch.global.L2 [%0];" ::"l"(ak - kTcAccLen / 4 + 32 * v));
-                    }
                 }
-                u64 ph[16];
-#if !QON_TC_PH_LATE
-                tc_phase_table(th, 1.f, ph);
-#endif
                 wait_on(bar_d_t, dpar);
                 tc_load_state(tDp, ps);
                 tc_load_state(tDl, lm);
@@ -365,11 +367,7 @@ hea_tc_rev_kernel(const HeaParams<float> p, const unsigned char* __restrict__ im
                         }
                         if constexpr (FREQ_GRAD) {
                             const int col = k * NQ + q;
-#if QON_TC_UV_REUSE
                             fv[2 * q] = gxv * uv[q];
-#else
-                            fv[2 * q] = gxv * __ldg((k < p.K0 ? u0row : u1row) + __ldg(p.uidx + col));
-#endif
                             fv[2 * q + 1] = gxv;
                         }
                     }
@@ -379,9 +377,10 @@ hea_tc_rev_kernel(const HeaParams<float> p, const unsigned char* __restrict__ im
                     }
                 }
                 if (k > 0) {
-#if QON_TC_PH_LATE
+                    // (computed here, not under the GEMM wait: measured 9.3 vs 9.9 ms per 1M-sample step — held across the
+                    // x-gradient the 32 table registers spill)
+                    u64 ph[16];
                     tc_phase_table(th, 1.f, ph);
-#endif
                     // conjugate phases; the scale restores |psi| = sA (the truncating accumulation shrinks both states
                     // by the same factor per GEMM), applied to lam as well
                     float nr4[4] = {0.f, 0.f, 0.f, 0.f};
@@ -425,10 +424,8 @@ hea_tc_rev_kernel(const HeaParams<float> p, const unsigned char* __restrict__ im
                     }
                 }
 #pragma unroll
-                for (int q = 0; q < NQ; ++q) {
-                    th[q] = thn[q];
-                    if constexpr (FREQ_GRAD && QON_TC_UV_REUSE) uv[q] = uvn[q];
-                }
+                for (int q = 0; q < NQ; ++q) uv[q] = un[q];
+                angles_from(k > 0 ? k - 1 : 0, uv, th);
             }
             // a barrier wait that timed out leaves garbage: poison this warp's partial sums so that the loss and
             // every gradient of the step read NaN instead of a plausible number

@@ -636,6 +636,7 @@ int run(const Job& j) {
     p.rowlen = pl.rowlen;
     p.K = K; p.S = pl.S; p.pauli = j.ham_kind; p.offset = (T)j.offset; p.coeff = (T)j.coeff;
     p.u0 = (const T*)j.u0; p.u1 = (const T*)j.u1; p.ldu0 = j.ldu0; p.ldu1 = j.ldu1; p.K0 = j.K0;
+    p.in0 = j.in0 > 0 ? j.in0 : 1; p.in1 = j.in1 > 0 ? j.in1 : 1;
     p.uidx = j.enc ? (const int*)(base + pl.off_i) : nullptr;
     p.fw = (const T*)j.fw; p.fb = (const T*)j.fb;
 

@@ -6,8 +6,8 @@ from ONE batch-summed outer product per block, taken at the block's output cut:
     cut after the rotations of sublayer s:  Y <- T Y T^+  with the sample-independent T of the sublayers behind it,
     moment of P_q there:  Im <lam|P_q|psi> summed over the batch  =  Im tr(P_q Y).
 Emulated here: the real 64 x 64 form of the outer product and how Y is read from it, the per-step power-of-two scale
-E >= max|g| that keeps g_b lam_b inside the f16 range, the exact 64-bit fixed-point batch accumulation (deterministic),
-and the conjugation chain of the moment kernel (same order of operations as tc_moment_kernel)."""
+E >= max|g| that keeps g_b lam_b inside the f16 range, fp32 tile accumulators summed in fp64, and the conjugation chain
+of the moment kernel (same order of operations as tc_moment_kernel)."""
 import os, sys
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
@@ -18,7 +18,6 @@ import tc_emulate_bwd as emub
 
 n, N = 5, 32
 SA = 32768.0
-FIX = 256.0
 
 
 def split16(v):
@@ -36,9 +35,9 @@ def real_rows(v):
 
 
 def outer_fixed(psi, lam, gt, exact):
-    """D[m][n'] = sum_b lam~[b][m] psi~[b][n'] per 128-sample tile (fp32 accumulator), tiles summed in 64-bit fixed point."""
+    """D[m][n'] = sum_b lam~[b][m] psi~[b][n'] per 128-sample tile (fp32 accumulator), tiles summed in fp64."""
     B = psi.shape[0]
-    acc = np.zeros((64, 64), np.int64)
+    acc = np.zeros((64, 64))
     for t0 in range(0, B, 128):
         P = real_rows(psi[t0:t0 + 128] * SA)
         L = real_rows(lam[t0:t0 + 128] * gt[t0:t0 + 128, None] * SA)
@@ -47,7 +46,7 @@ def outer_fixed(psi, lam, gt, exact):
         else:
             Ph, Pl = split16(P); Lh, Ll = split16(L)
             D = (Lh.T @ Ph + Lh.T @ Pl + Ll.T @ Ph).astype(np.float32)
-        acc += np.rint(D.astype(np.float64) * FIX).astype(np.int64)
+        acc += D.astype(np.float64)
     return acc
 
 
@@ -139,7 +138,7 @@ def tc_backward_outer(x, w, depths, hdiag, gout, exact=False):
     gx = np.zeros((B, n * K)); mom = np.zeros((S, 15))
     for k in reversed(range(K)):
         acc = outer_fixed(psi, lam, gt, exact)
-        Y = y_from_d(acc, E * hmax / (SA * SA * FIX))
+        Y = y_from_d(acc, E * hmax / (SA * SA))
         mom[s0s[k]:s0s[k] + depths[k]] = block_moments(Y, w, s0s[k], depths[k], k < K - 1)
         Minv = np.conj(Ms[k].T)
         psi, lam = psi @ Minv.T, lam @ Minv.T

@@ -1040,3 +1040,102 @@ def test_host_fed_training_equals_device_resident(cuda_device):
     m2.double()
     with pytest.raises(RuntimeError, match="no longer alias"):
         t2.step(tuple(a.to(dev) for a in batches[0][0]), batches[0][1].to(dev))
+
+
+def _tc_backward(lib, version, g, x, w, depths, dev, need_gx=False):
+    """hea_expval_backward on the tensor-core tier, training-step version 1 (GEMM-form weight gradients, default),
+    2 (per-sublayer Pauli-string moments, two kernels) or 3 (the same in one kernel)."""
+    from quanonet_b200.ops import hea_expval_backward
+    t = lambda a: torch.tensor(a, dtype=torch.float32, device=dev)
+    lib.qon_tensor_tier(version, 0, None, None)
+    o, gx, gw = hea_expval_backward(t(g), t(x), t(w), 5, list(depths), None, 0, 0.0, 1.0, 0, need_gx)
+    torch.cuda.synchronize()
+    return o.double().cpu().numpy()[:, 0], None if gx is None else gx.double().cpu().numpy(), gw.double().cpu().numpy()
+
+
+@pytest.mark.parametrize("B", [1, 127, 129, 300, 40000])
+def test_tensor_tier_gemm_gradients_vs_oracle_ragged_batches(cuda_device, B):
+    """GEMM-form weight gradients (csrc/hea_tc3.cuh): batch sizes around the 128-sample tile and the 256-sample CTA
+    (partial tiles contribute nothing, idle accumulator slots hold zeros), more tiles than one round of the grid."""
+    from oracle import hea_oracle as orc
+    from quanonet_b200 import _lib
+    lib = _lib.load()
+    n, depths = 5, [2, 1, 3]
+    K, S = len(depths), sum(depths)
+    rng = np.random.default_rng(B)
+    x = rng.uniform(-np.pi, np.pi, (B, n * K)); w = rng.uniform(-np.pi, np.pi, (S, 3, n)); g = rng.standard_normal(B)
+    try:
+        o, gx, gw = _tc_backward(lib, 1, g, x, w, depths, cuda_device, need_gx=True)
+    finally:
+        lib.qon_tensor_tier(1, 12289, None, None)
+    nref = min(B, 400)
+    e_ref, gx_ref, _ = orc.hea_forward_backward(x[:nref], w, n, [(n, d) for d in depths], orc.ham_from_bound(n), g[:nref])
+    _, _, gw_ref = orc.hea_forward_backward(x, w, n, [(n, d) for d in depths], orc.ham_from_bound(n), g) if B <= 400 else (None, None, None)
+    assert rel_l2(o[:nref], e_ref) < TOL_F32 and rel_l2(gx[:nref], gx_ref) < TOL_F32
+    if gw_ref is not None:
+        assert rel_l2(gw, gw_ref) < TOL_F32
+    else:       # full batch: against the FFMA2 register kernels
+        from quanonet_b200.ops import hea_expval_backward
+        t = lambda a: torch.tensor(a, dtype=torch.float32, device=cuda_device)
+        lib.qon_tensor_tier(0, 12289, None, None)
+        try:
+            _, _, gw_r = hea_expval_backward(t(g), t(x), t(w), n, depths, None, 0, 0.0, 1.0, 0, False)
+        finally:
+            lib.qon_tensor_tier(1, 12289, None, None)
+        assert rel_l2(gw, gw_r.double().cpu().numpy()) < 2 * TOL_F32
+
+
+@pytest.mark.parametrize("scale", [1e-30, 1e-6, 1.0, 3e4, 1e30])
+def test_tensor_tier_gemm_gradients_upstream_gradient_range(cuda_device, scale):
+    """The outer-product operands carry g_b / E with E the power of two above max |g_b|: gradients must stay at parity
+    over the whole fp32 range of upstream gradients, including a batch whose |g_b| span 12 decades."""
+    from quanonet_b200 import _lib
+    lib = _lib.load()
+    n, depths, B = 5, [2, 2, 1], 700
+    K, S = len(depths), sum(depths)
+    rng = np.random.default_rng(5)
+    x = rng.uniform(-np.pi, np.pi, (B, n * K)); w = rng.uniform(-np.pi, np.pi, (S, 3, n))
+    g = rng.standard_normal(B) * scale * 10.0 ** rng.uniform(-12, 0, B)
+    try:
+        o1, gx1, gw1 = _tc_backward(lib, 1, g, x, w, depths, cuda_device, need_gx=True)
+        o0, gx0, gw0 = _tc_backward(lib, 0, g, x, w, depths, cuda_device, need_gx=True)       # FFMA2 register kernels
+    finally:
+        lib.qon_tensor_tier(1, 12289, None, None)
+    assert np.isfinite(gw1).all() and np.isfinite(gx1).all()
+    assert rel_l2(gw1, gw0) < 2 * TOL_F32 and rel_l2(gx1, gx0) < 2 * TOL_F32 and rel_l2(o1, o0) < 2 * TOL_F32
+
+
+def test_tensor_tier_gemm_gradients_zero_and_nan_upstream(cuda_device):
+    """All-zero upstream gradients give exactly zero gradients (E degenerates to the smallest normal number); one NaN
+    poisons the weight gradients, as summing over the batch does in the reference's autograd."""
+    from quanonet_b200 import _lib
+    lib = _lib.load()
+    n, depths, B = 5, [1, 2], 300
+    rng = np.random.default_rng(6)
+    x = rng.uniform(-np.pi, np.pi, (B, n * 2)); w = rng.uniform(-np.pi, np.pi, (3, 3, n))
+    try:
+        _, gx, gw = _tc_backward(lib, 1, np.zeros(B), x, w, depths, cuda_device, need_gx=True)
+        assert not gw.any() and not gx.any()
+        g = rng.standard_normal(B); g[17] = np.nan
+        _, _, gwn = _tc_backward(lib, 1, g, x, w, depths, cuda_device)
+        assert np.isnan(gwn).all()
+    finally:
+        lib.qon_tensor_tier(1, 12289, None, None)
+
+
+def test_tensor_tier_training_step_versions_agree(cuda_device):
+    """The three tensor-core training-step variants — GEMM-form weight gradients (default), per-sublayer string moments
+    in two kernels, the same in one kernel — produce the same gradients (kept for A/B runs: none may rot)."""
+    from quanonet_b200 import _lib
+    lib = _lib.load()
+    n, depths, B = 5, [2] * 7 + [1, 3], 5000
+    K, S = len(depths), sum(depths)
+    rng = np.random.default_rng(8)
+    x = rng.uniform(-np.pi, np.pi, (B, n * K)); w = rng.uniform(-np.pi, np.pi, (S, 3, n)); g = rng.standard_normal(B)
+    try:
+        res = {v: _tc_backward(lib, v, g, x, w, depths, cuda_device, need_gx=True) for v in (1, 2, 3)}
+    finally:
+        lib.qon_tensor_tier(1, 12289, None, None)
+    for v in (2, 3):
+        for a, b in zip(res[1], res[v]):
+            assert rel_l2(a, b) < TOL_F32, v

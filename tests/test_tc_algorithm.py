@@ -52,3 +52,24 @@ def test_adjoint_sweep_composites_and_string_moments():
         o, gx, gw = emub.tc_backward(x, w, depths, hd, g)
         rel = lambda a, b: np.linalg.norm(a - b) / np.linalg.norm(b)
         assert rel(o, o_ref) < 1e-12 and rel(gx, gx_ref) < 1e-12 and rel(gw, gw_ref) < 1e-12, depths
+
+
+def test_gemm_form_weight_gradients():
+    """csrc/hea_tc3.cuh: one batch-summed outer product per block (real 64 x 64 form, f16 hi/lo operands, power-of-two
+    gradient scale, fp32 tile accumulators) and the conjugation chain of tc_moment_kernel, against the fp64 oracle."""
+    from oracle import hea_oracle as orc
+    import tc_emulate_outer as emo
+    rng = np.random.default_rng(9)
+    n = 5
+    for depths, B, gs in (([1], 5, 1.0), ([2, 1], 130, 1e-4), ([1, 3, 2], 300, 50.0)):
+        K, S = len(depths), sum(depths)
+        x = rng.uniform(-np.pi, np.pi, (B, n * K))
+        w = rng.uniform(-np.pi, np.pi, (S, 3, n))
+        g = rng.normal(size=B) * gs
+        hd = np.array([n - 2 * bin(z).count("1") for z in range(32)], float)
+        o_ref, gx_ref, gw_ref = orc.hea_forward_backward(x, w, n, [(n, d) for d in depths], orc.ham_from_bound(n), g)
+        rel = lambda a, b: np.linalg.norm(a - b) / np.linalg.norm(b)
+        o, gx, gw = emo.tc_backward_outer(x, w, depths, hd, g, exact=True)
+        assert rel(o, o_ref) < 1e-12 and rel(gx, gx_ref) < 1e-12 and rel(gw, gw_ref) < 5e-7, depths     # fp32 operand rows
+        o, gx, gw = emo.tc_backward_outer(x, w, depths, hd, g, exact=False)
+        assert rel(gw, gw_ref) < 2e-6, depths                                                             # the kernels' bar is 1e-5
