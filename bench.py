@@ -464,12 +464,13 @@ def run_b200(args):
                     "timer": "max(CUDA events, host wall clock) over the K steps, max over ranks"},
             # this library's kernels per step: prep, circuit kernel, finalize (+ finalize_enc) — with N > 1 the
             # finalize kernel is also the all-reduce (finalize_exchange_kernel), else one peer all-reduce kernel more;
-            # the tensor-core tier adds its two operand-image prep kernels and runs the step as forward-only + reverse-only kernels
+            # the tensor-core tier adds its two operand-image prep kernels, runs the step as forward-only + reverse-only
+            # kernels and turns the batch-summed outer products into Pauli moments in one more (tc_moment_kernel)
             "gpu_launches": ((3 if getattr(trainer, "_fused_exchange", False) else
-                              (4 if trainer.fused_encoding else 3) + (1 if world > 1 else 0)) + (3 if tc_on else 0)) * K,
+                              (4 if trainer.fused_encoding else 3) + (1 if world > 1 else 0)) + (4 if tc_on else 0)) * K,
             "roofline": {"bound": "fp32", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                          "frac": achieved / peak if peak else None, "traffic": traffic,
-                         "kernel": ("hea_tc_kernel: forward-only + reverse-only gradient kernel<grad%s> (tcgen05 block-unitary GEMMs + FFMA2 phases / Pauli moments; +prep, finalize)"
+                         "kernel": ("hea_tc_kernel<forward> + hea_tc_rev_kernel<grad%s> (tcgen05: block-unitary GEMMs, batch-summed outer products for the weight gradients; FFMA2 phases; +prep, tc_moment_kernel, finalize)"
                                     if tc_on else "hea_reg_kernel<float,5,0,grad%s> (+prep, finalize)") % (
                              ",fused-encoding" if trainer.fused_encoding else ""), "kernel_ms": kern_ms,
                          "flops_per_sample": f_all, "peak_source": "FFMA probe measured on this GPU in this run "

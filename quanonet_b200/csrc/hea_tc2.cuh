@@ -392,6 +392,13 @@ hea_tc_kernel(const HeaParams<float> p, const unsigned char* __restrict__ images
         float* frow = GRAD ? mrow + (int64_t)p.S * 16 : nullptr;
         float* srow = GRAD ? frow + (int64_t)p.K * 16 : nullptr;
 
+        int qm0[NQ], qm1[NQ];        // q % in of the two input sources
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+            qm0[q] = ENC != 0 ? q % p.in0 : 0;
+            qm1[q] = ENC != 0 ? q % p.in1 : 0;
+        }
+
         for (int64_t round = 0; round < rounds; ++round) {
             const int64_t tile = (round * gridDim.x + blockIdx.x) * NT + t;
             const int64_t b = tile * 128 + quarter * 32 + lane;
@@ -400,19 +407,38 @@ hea_tc_kernel(const HeaParams<float> p, const unsigned char* __restrict__ images
             const float* xrow = ENC == 0 ? p.x + bc * p.ldx : nullptr;
             const float* u0row = ENC != 0 && p.u0 ? p.u0 + bc * p.ldu0 : nullptr;
             const float* u1row = ENC != 0 ? p.u1 + bc * p.ldu1 : nullptr;
-            auto load_angles = [&](int k, float(&th)[NQ]) {
+            // The angles of a block are loaded ONE BLOCK AHEAD as raw inputs and turned into angles when the block starts
+            // (load_angles_late): an in-order warp stalls at the first use of a load.  The input column of angle c is
+            // uidx[c] = local column % in (prep kernel, qon_capi.cu), recomputed here from the block index so that the
+            // gather does not hang on a load of the index table.
+            auto load_inputs = [&](int k, float(&un)[NQ]) {
                 if constexpr (ENC == 0) {
 #pragma unroll
-                    for (int q = 0; q < NQ; ++q) th[q] = __ldg(xrow + (int64_t)k * NQ + q);
+                    for (int q = 0; q < NQ; ++q) un[q] = __ldg(xrow + (int64_t)k * NQ + q);
                 } else {
-                    const float* ur = k < p.K0 ? u0row : u1row;
+                    const bool s0 = k < p.K0;
+                    const float* ur = s0 ? u0row : u1row;
+                    const int in = s0 ? p.in0 : p.in1;
+                    const int base = ((s0 ? k : k - p.K0) * NQ) % in;
 #pragma unroll
                     for (int q = 0; q < NQ; ++q) {
-                        const int col = k * NQ + q;
-                        const float u = __ldg(ur + __ldg(p.uidx + col));
-                        th[q] = fmaf(u, __ldg(p.fw + col), p.fb ? __ldg(p.fb + col) : 0.f);
+                        int idx = base + (s0 ? qm0[q] : qm1[q]);
+                        if (idx >= in) idx -= in;
+                        un[q] = __ldg(ur + idx);
                     }
                 }
+            };
+            auto angles_from = [&](int k, const float(&un)[NQ], float(&th)[NQ]) {
+#pragma unroll
+                for (int q = 0; q < NQ; ++q) {
+                    if constexpr (ENC == 0) th[q] = un[q];
+                    else th[q] = fmaf(un[q], __ldg(p.fw + k * NQ + q), p.fb ? __ldg(p.fb + k * NQ + q) : 0.f);
+                }
+            };
+            auto load_angles = [&](int k, float(&th)[NQ]) {      // both steps at once (the reverse sweep of this kernel)
+                float un[NQ];
+                load_inputs(k, un);
+                angles_from(k, un, th);
             };
             const bool dump = DBG && dbg && blockIdx.x == 0 && t == 0 && round == 0;
             const int drow = quarter * 32 + lane;
@@ -422,8 +448,8 @@ hea_tc_kernel(const HeaParams<float> p, const unsigned char* __restrict__ images
             if constexpr (!SPLIT) {
             load_angles(0, th);
             for (int k = 0; k < p.K; ++k) {
-                float thn[NQ];
-                load_angles(k + 1 < p.K ? k + 1 : k, thn);
+                float un[NQ];
+                load_inputs(k + 1 < p.K ? k + 1 : k, un);
                 u64 ph[16];
                 tc_phase_table(th, 1.f, ph);
                 if (k > 0) wait_d();
@@ -455,8 +481,7 @@ hea_tc_kernel(const HeaParams<float> p, const unsigned char* __restrict__ images
                     tc::tmem_st8(tAp + 32u + 8u * c, alo);
                 }
                 signal_a();
-#pragma unroll
-                for (int q = 0; q < NQ; ++q) th[q] = thn[q];
+                angles_from(k + 1 < p.K ? k + 1 : k, un, th);
             }
             wait_d();
             }

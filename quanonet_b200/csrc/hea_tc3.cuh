@@ -206,9 +206,9 @@ hea_tc_rev_kernel(const HeaParams<float> p, const unsigned char* __restrict__ im
         const uint32_t tAl = tAp + 64u;                                              // A lam
         const int srow_t = quarter * 32 + lane;                                      // sample row inside the tile
         unsigned char* op = tc_smem + (size_t)t * G::TILE_SMEM + (srow_t >> 3) * 1024 + (srow_t & 7) * 16;
-        const uint32_t bar_a_t = tc::smem_u32(&bar_a[t]), bar_a2_t = tc::smem_u32(&bar_a2[t]);
+        const uint32_t bar_a_t = tc::smem_u32(&bar_a[t]), bar_a2_t = tc::smem_u32(&bar_a2[t]), bar_x_t = tc::smem_u32(&bar_x[t]);
         const uint32_t bar_d_t = tc::smem_u32(&bar_d[t]), bar_g_t = tc::smem_u32(&bar_g[t]);
-        uint32_t dpar = 0, gpar = 0;
+        uint32_t dpar = 0, gpar = 0, xpar = 0;
         bool dead = false;
         auto wait_on = [&](uint32_t bar, uint32_t& par) {
             if (!dead && !tc_wait(bar, par, err)) dead = true;
@@ -340,46 +340,23 @@ hea_tc_rev_kernel(const HeaParams<float> p, const unsigned char* __restrict__ im
                 tc_store_operand2<true>(tAl, op + 32768, op + 49152, lm);
                 signal(bar_a2_t);
                 // this slot's running sums of block k (written a whole round ago): loaded now, added when the outer product
-                // is drained (an L2 prefetch of block k-1's at this point measured 4 % SLOWER: 8.93 vs 8.56 ms per step)
+                // is drained.  The slots' accumulators (2 x 148 x K x 8 KB = 142 MB at K = 60) cycle through L2 once per round
+                // and are re-fetched from HBM (ncu: 4.5 GB read + 4.0 GB written per 1M-sample step, 16 % of the HBM
+                // bandwidth over the kernel).  Tried and dropped: an L2 prefetch of block k-1's lines from here (4 % slower),
+                // evict_last / evict_first fractional L2 policies on these accesses (no change in traffic or time).
                 float4* ak = reinterpret_cast<float4*>(acc + ((size_t)(blockIdx.x * NT + t) * p.K + k) * kTcAccLen) + quarter * 128 + lane;
                 float4 old4[4];
                 if (round > 0) {
 #pragma unroll
                     for (int v = 0; v < 4; ++v) old4[v] = __ldcg(ak + 32 * v);
                 }
-                wait_on(bar_d_t, dpar);
+                // psi first: its un-apply GEMM completes (bar_x) while the lam GEMM still runs, so the norm, the phase table
+                // and psi's conjugate phases are computed under the lam GEMM
+                wait_on(bar_x_t, xpar);
                 tc_load_state(tDp, ps);
-                tc_load_state(tDl, lm);
-                // Hadamard basis, right after the block's encoding layer
-                if constexpr (WANT_GX) {
-                    float gq[5];
-                    tc_xgrad(ps, lm, gq);
-                    float fv[FREQ_GRAD ? 16 : 1];
-                    if constexpr (FREQ_GRAD) {
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) fv[i] = 0.f;
-                    }
-#pragma unroll
-                    for (int q = 0; q < NQ; ++q) {
-                        const float gxv = gq[q] * xscale;
-                        if constexpr (NEED_GX) {
-                            if (valid) gxrow[(int64_t)k * NQ + q] = gxv;
-                        }
-                        if constexpr (FREQ_GRAD) {
-                            const int col = k * NQ + q;
-                            fv[2 * q] = gxv * uv[q];
-                            fv[2 * q + 1] = gxv;
-                        }
-                    }
-                    if constexpr (FREQ_GRAD) {
-                        const float ft = butterfly_reduce<float, 16>(fv, lane);
-                        if ((lane & 1) == 0) atomicAdd(frow + (int64_t)k * 16 + (lane >> 1), ft);
-                    }
-                }
+                u64 ph[16];
+                float inv_c2 = 1.f;
                 if (k > 0) {
-                    // (computed here, not under the GEMM wait: measured 9.3 vs 9.9 ms per 1M-sample step — held across the
-                    // x-gradient the 32 table registers spill)
-                    u64 ph[16];
                     tc_phase_table(th, 1.f, ph);
                     // conjugate phases; the scale restores |psi| = sA (the truncating accumulation shrinks both states
                     // by the same factor per GEMM), applied to lam as well
@@ -389,11 +366,42 @@ hea_tc_rev_kernel(const HeaParams<float> p, const unsigned char* __restrict__ im
                         const float re = __uint_as_float(ps[2 * z]), im = __uint_as_float(ps[2 * z + 1]);
                         nr4[z & 3] = fmaf(re, re, fmaf(im, im, nr4[z & 3]));
                     }
-                    const float corr = kTcSA * rsqrtf((nr4[0] + nr4[1]) + (nr4[2] + nr4[3]));
+                    const float nr = (nr4[0] + nr4[1]) + (nr4[2] + nr4[3]);
+                    const float corr = kTcSA * rsqrtf(nr);
+                    inv_c2 = nr * (1.f / (kTcSA * kTcSA));
 #pragma unroll
                     for (int i = 0; i < 16; ++i) ph[i] = mul2<0>(corr, ph[i]);
                     tc_apply_phases<true>(ps, ph);
-                    tc_apply_phases<true>(lm, ph);
+                }
+                wait_on(bar_d_t, dpar);
+                tc_load_state(tDl, lm);
+                if (k > 0) tc_apply_phases<true>(lm, ph);
+                // encoding-angle gradients of block k (Hadamard basis, at the block's encoding layer):
+                // sum_z (1 - 2 z_q) Im(conj(mu_z) phi_z) is unchanged by the common conjugate phases up to their scale corr^2
+                if constexpr (WANT_GX) {
+                    float gq[5];
+                    tc_xgrad(ps, lm, gq);
+                    float fv[FREQ_GRAD ? 16 : 1];
+                    if constexpr (FREQ_GRAD) {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) fv[i] = 0.f;
+                    }
+                    const float xs = xscale * inv_c2;
+#pragma unroll
+                    for (int q = 0; q < NQ; ++q) {
+                        const float gxv = gq[q] * xs;
+                        if constexpr (NEED_GX) {
+                            if (valid) gxrow[(int64_t)k * NQ + q] = gxv;
+                        }
+                        if constexpr (FREQ_GRAD) {
+                            fv[2 * q] = gxv * uv[q];
+                            fv[2 * q + 1] = gxv;
+                        }
+                    }
+                    if constexpr (FREQ_GRAD) {
+                        const float ft = butterfly_reduce<float, 16>(fv, lane);
+                        if ((lane & 1) == 0) atomicAdd(frow + (int64_t)k * 16 + (lane >> 1), ft);
+                    }
                 }
                 // drain the outer product of block k.  Warp `quarter` owns rows 16 quarter .. + 15 of D_G (lanes 0..15 of its
                 // subpartition) = amplitudes i = 8 quarter .. + 7 of lam, real rows then imaginary rows; thread T of the
