@@ -70,4 +70,11 @@ __device__ __forceinline__ u64 fma2_vv(u64 a, u64 b, u64 c) {
     return d;
 }
 
+// packed a + b (one FADD2)
+__device__ __forceinline__ u64 add2(u64 a, u64 b) {
+    u64 d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+
 }  // namespace qon

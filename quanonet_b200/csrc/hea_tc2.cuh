@@ -252,6 +252,28 @@ __device__ __forceinline__ float tc_sample_g(const HeaParams<float>& p, float e,
     return p.gout ? __ldg(p.gout + b) : 0.f;
 }
 
+// the same five sums from ONE packed product per amplitude and a pairwise tree: with t_z = Im(conj(mu_z) phi_z),
+//   S_q = sum_z (1 - 2 z_q) t_z = T - 2 O_q,   T = sum_z t_z,   O_q = sum over z with z_q = 1,
+// level q pairs the partial sums that differ in bit q: 32 products + 57 packed adds instead of 160 FFMA2
+__device__ __forceinline__ void tc_xgrad_tree(const uint32_t (&ps)[64], const uint32_t (&lm)[64], float (&gq)[5]) {
+    u64 u[32];
+#pragma unroll
+    for (int z = 0; z < 32; ++z) u[z] = fma2_vp<3>(tc_pair(lm, z), tc_pair(ps, z), 0ull);    // (mu_r phi_i, -mu_i phi_r)
+    u64 odd[5];
+    static_for<5>([&](auto Qc) {
+        constexpr int q = decltype(Qc)::value;
+        constexpr int n = 32 >> q;                 // live partial sums at this level
+        odd[q] = u[1];
+#pragma unroll
+        for (int j = 1; j < n / 2; ++j) odd[q] = add2(odd[q], u[2 * j + 1]);
+#pragma unroll
+        for (int j = 0; j < n / 2; ++j) u[j] = add2(u[2 * j], u[2 * j + 1]);
+    });
+    const float T = lo2(u[0]) + hi2(u[0]);
+#pragma unroll
+    for (int q = 0; q < 5; ++q) gq[q] = fmaf(-2.f, lo2(odd[q]) + hi2(odd[q]), T);
+}
+
 // bounded mbarrier wait without busy work: try_wait suspends in hardware for up to ~20 us per probe
 __device__ __forceinline__ bool tc_wait(uint32_t bar, uint32_t parity, int* err) {
     for (int it = 0; it < 100000; ++it) {

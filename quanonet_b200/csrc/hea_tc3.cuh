@@ -236,6 +236,7 @@ hea_tc_rev_kernel(const HeaParams<float> p, const unsigned char* __restrict__ im
         float* frow = mrow + (int64_t)p.S * 16;
         float* srow = frow + (int64_t)p.K * 16;
 
+        const int step0 = ENC != 0 ? NQ % p.in0 : 0, step1 = ENC != 0 ? NQ % p.in1 : 0;
         int qm0[NQ], qm1[NQ];        // q % in of the two input sources
 #pragma unroll
         for (int q = 0; q < NQ; ++q) {
@@ -257,6 +258,7 @@ hea_tc_rev_kernel(const HeaParams<float> p, const unsigned char* __restrict__ im
             // two warps per scheduler nobody covers for it.  The input column of angle c is uidx[c] = local column % in
             // (prep kernel, qon_capi.cu); it is recomputed from the block index here, so the gather does not hang on a
             // load of the index table.
+            int cbase = 0, cblock = -2;      // (5 k') mod in of the block loaded last: stepped down instead of divided
             auto load_inputs = [&](int k, float(&un)[NQ]) {
                 if constexpr (ENC == 0) {
 #pragma unroll
@@ -265,7 +267,14 @@ hea_tc_rev_kernel(const HeaParams<float> p, const unsigned char* __restrict__ im
                     const bool s0 = k < p.K0;
                     const float* ur = s0 ? u0row : u1row;
                     const int in = s0 ? p.in0 : p.in1;
-                    const int base = ((s0 ? k : k - p.K0) * NQ) % in;
+                    if (k == cblock - 1 && (k + 1 < p.K0) == s0) {      // one block down inside the same source
+                        cbase -= s0 ? step0 : step1;
+                        if (cbase < 0) cbase += in;
+                    } else if (k != cblock) {
+                        cbase = ((s0 ? k : k - p.K0) * NQ) % in;
+                    }
+                    cblock = k;
+                    const int base = cbase;
 #pragma unroll
                     for (int q = 0; q < NQ; ++q) {
                         int idx = base + (s0 ? qm0[q] : qm1[q]);
@@ -380,7 +389,7 @@ hea_tc_rev_kernel(const HeaParams<float> p, const unsigned char* __restrict__ im
                 // sum_z (1 - 2 z_q) Im(conj(mu_z) phi_z) is unchanged by the common conjugate phases up to their scale corr^2
                 if constexpr (WANT_GX) {
                     float gq[5];
-                    tc_xgrad(ps, lm, gq);
+                    tc_xgrad_tree(ps, lm, gq);
                     float fv[FREQ_GRAD ? 16 : 1];
                     if constexpr (FREQ_GRAD) {
 #pragma unroll
