@@ -184,12 +184,15 @@ int qon_encoded_mse_step_dp(const void* u0, int64_t ldu0, int in0, int K0, const
                             int diag_order, double ham_offset, double ham_coeff, int ham_kind, void* workspace,
                             size_t workspace_bytes, void* stream);
 
-/* Tensor-core tier (n = 5, fp32, diagonal observable — csrc/hea_tc.cuh, hea_tc2.cuh): every entry point above
+/* Tensor-core tier (n = 5, fp32, diagonal observable — csrc/hea_tc.cuh, hea_tc2.cuh, hea_tc3.cuh): every entry point above
  * routes batches of at least `min_batch` samples to it: the ansatz sublayers of a block (sample-independent in the
  * reference, core/quantum_circuits_tq.py:89-101) pre-fused into one 32x32 unitary and applied as split-f16 GEMMs on
- * tcgen05 tensor cores, the RX encoding layers as diagonal phases in the Hadamard basis; same results to the 1e-5
+ * tcgen05 tensor cores, the RX encoding layers as diagonal phases in the Hadamard basis; in gradient calls the weight
+ * gradients come from one batch-summed outer product per block on the tensor cores as well; same results to the 1e-5
  * norm-relative bar.  On by default (QON_TC=0 in the environment disables it; QON_TC_MIN_B sets the threshold).
- *   enable     1 = on, 0 = off (the FFMA2 register kernels serve every batch), -1 = leave unchanged
+ *   enable     1 = on, 0 = off (the FFMA2 register kernels serve every batch), -1 = leave unchanged;
+ *              2 / 3 = on, with the earlier formulations of the gradient step (per-sublayer Pauli-string moments in
+ *              two kernels / in one kernel), kept for A/B measurements
  *   min_batch  smallest batch routed to the tier (default 12289); < 0 = leave unchanged
  *   debug_state / error_flag: device pointers for kernel bring-up (state dump of the first tile; protocol
  *   time-out flag), NULL in production — a time-out poisons the outputs with NaN, it never hangs.

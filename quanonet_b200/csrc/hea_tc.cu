@@ -14,9 +14,10 @@ static int tc_grad_grid(int64_t B, int sms) {
 
 size_t tc_workspace_bytes(int K, int S, int64_t B, int sms) {
     // operand images + flags (error word, max |g| bits) + (training step) one 256-byte state row per sample + the
-    // outer-product accumulators of the GEMM-form weight gradients: one per (CTA, tile slot) and block
+    // outer-product accumulators of the GEMM-form weight gradients: one per (CTA, tile slot) and block, + their fp64 sums
     return (size_t)(K + S) * kTcImgBytes + 256 +
-           (B > 0 ? (size_t)B * 256 + (size_t)2 * tc_grad_grid(B, sms) * K * kTcAccLen * sizeof(float) : 0);
+           (B > 0 ? (size_t)B * 256 + (size_t)2 * tc_grad_grid(B, sms) * K * kTcAccLen * sizeof(float) +
+                        (size_t)K * kTcAccLen * sizeof(double) : 0);
 }
 
 static int tc_flags() {
@@ -94,7 +95,9 @@ cudaError_t tc_launch(int mode, int version, int sms, const HeaParams<float>& p,
             default: return cudaErrorInvalidValue;
         }
         if (e != cudaSuccess) return e;
-        tc_moment_kernel<<<p.K, 1024, 0, st>>>(gacc, 2 * g, gmax, p.hdiag, w, p.K, dp, p.mpart);
+        double* ysum = reinterpret_cast<double*>(gacc + (size_t)2 * g * p.K * kTcAccLen);
+        tc_slot_reduce_kernel<<<p.K * 8, 256, 0, st>>>(gacc, 2 * g, p.K, ysum);
+        tc_moment_kernel<<<p.K, 1024, 0, st>>>(ysum, gmax, p.hdiag, w, p.K, dp, p.mpart);
         return cudaGetLastError();
     }
     if (version == 3 || dbg) {      // the whole step in ONE kernel (forward sweep on the gradient kernel's 2 tiles)

@@ -458,11 +458,33 @@ hea_tc_rev_kernel(const HeaParams<float> p, const unsigned char* __restrict__ im
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// slot sums: ysum[k][f] = sum over the slots of acc[slot][k][f], in slot order, in fp64.  grid = K * 8 CTAs of 256
+// threads (thread = one float of a block's 2,048; a slot's floats are contiguous, so a warp reads 128-byte lines) —
+// the 142 MB of accumulators stream through all SMs instead of through the moment kernel's K CTAs.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) tc_slot_reduce_kernel(const float* __restrict__ acc, int nslots, int K,
+                                                             double* __restrict__ ysum) {
+    const int k = blockIdx.x >> 3, f = ((blockIdx.x & 7) << 8) + threadIdx.x;
+    const float* a = acc + (size_t)k * kTcAccLen + f;
+    const size_t stride = (size_t)K * kTcAccLen;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;      // four chains, combined in a fixed order
+    int sl = 0;
+    for (; sl + 4 <= nslots; sl += 4) {
+        s0 += (double)__ldcs(a + (size_t)sl * stride);
+        s1 += (double)__ldcs(a + (size_t)(sl + 1) * stride);
+        s2 += (double)__ldcs(a + (size_t)(sl + 2) * stride);
+        s3 += (double)__ldcs(a + (size_t)(sl + 3) * stride);
+    }
+    for (; sl < nslots; ++sl) s0 += (double)__ldcs(a + (size_t)sl * stride);
+    ysum[(size_t)k * kTcAccLen + f] = (s0 + s1) + (s2 + s3);
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // moments from the outer products: grid = K CTAs of 1,024 threads (thread = one entry of the 32 x 32 complex Y_k,
-// fp64 in shared memory; the slots' partial sums are added in slot order).  Adds the 15 moments of every sublayer of block k to partial row 0 (the finalize kernels
+// fp64 in shared memory).  Adds the 15 moments of every sublayer of block k to partial row 0 (the finalize kernels
 // sum the rows): mrow0[s * 16 + 3 q + {0, 1, 2}] += Im tr({X, Y, Z}_q Y) at the cut after the rotations of sublayer s.
 // ---------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) tc_moment_kernel(const float* __restrict__ acc, int nslots, const unsigned* __restrict__ gmax,
+__global__ void __launch_bounds__(1024) tc_moment_kernel(const double* __restrict__ ysum, const unsigned* __restrict__ gmax,
                                                          const float* __restrict__ hdiag, const float* __restrict__ w,
                                                          int K, DepthPack dp, float* __restrict__ mrow0) {
     constexpr int n = 5, N = 32;
@@ -481,12 +503,7 @@ __global__ void __launch_bounds__(1024) tc_moment_kernel(const float* __restrict
         // T = 4 (i & 7) + (j & 3), float4 number (j >> 3), components 2 ((j >> 2) & 1) + {0: Re, 1: Im}
         const int j = r, i = c;
         const size_t idx = ((size_t)((i >> 3) * 4 + (j >> 3)) * 32 + 4 * (i & 7) + (j & 3)) * 4 + 2 * ((j >> 2) & 1);
-        double re = 0.0, im = 0.0;
-        for (int sl = 0; sl < nslots; ++sl) {
-            const float2 v = __ldcg(reinterpret_cast<const float2*>(acc + ((size_t)sl * K + k) * kTcAccLen + idx));
-            re += (double)v.x;
-            im += (double)v.y;
-        }
+        const double re = ysum[(size_t)k * kTcAccLen + idx], im = ysum[(size_t)k * kTcAccLen + idx + 1];
         yr[j][i] = re * scale;
         yi[j][i] = im * scale;
     }
