@@ -47,11 +47,10 @@ __host__ __device__ constexpr int tc_b_offset(int nn, int kk) {
 //   B[2j][2i] = Re M_ij, B[2j+1][2i] = -Im M_ij, B[2j][2i+1] = Im M_ij, B[2j+1][2i+1] = Re M_ij,
 // stored as Bt[nn = 2i + c'][kk = 2j + c] (K-major).
 // ---------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(32) tc_prep_kernel(const float* __restrict__ w, int K, DepthPack dp,
-                                                     unsigned char* __restrict__ bimg) {
+__device__ __forceinline__ void tc_prep_body(const float* __restrict__ w, int K, const DepthPack& dp,
+                                             unsigned char* __restrict__ bimg, int k, double (*vr)[33], double (*vi)[33]) {
     constexpr int n = 5, N = 32;
-    __shared__ double vr[N][N + 1], vi[N][N + 1];
-    const int k = blockIdx.x, j = threadIdx.x;
+    const int j = threadIdx.x;
     int s0 = 0;
     for (int kk = 0; kk < k; ++kk) s0 += dp.d[kk];
     const int d = dp.d[k];
@@ -121,6 +120,11 @@ __global__ void __launch_bounds__(32) tc_prep_kernel(const float* __restrict__ w
         put(2 * i + 1, 2 * j, im);
         put(2 * i + 1, 2 * j + 1, re);
     }
+}
+__global__ void __launch_bounds__(32) tc_prep_kernel(const float* __restrict__ w, int K, DepthPack dp,
+                                                     unsigned char* __restrict__ bimg) {
+    __shared__ double vr[32][33], vi[32][33];
+    tc_prep_body(w, K, dp, bimg, blockIdx.x, vr, vi);
 }
 
 // ---------------------------------------------------------------------------------------------------------

@@ -59,14 +59,14 @@ __device__ __forceinline__ u64 tc_pair(const uint32_t (&r)[64], int z) {
 // so one operand split per block serves all its GEMMs.
 // ---------------------------------------------------------------------------------------------------------
 // per_block (hea_tc3.cuh): grid = K CTAs, image K-1-k = the whole-block un-apply matrix C_{s0(k)} = M_k^+.
-__global__ void __launch_bounds__(32) tc_prep_rev_kernel(const float* __restrict__ w, int K, int S, DepthPack dp,
-                                                         unsigned char* __restrict__ rimg, int per_block) {
+__device__ __forceinline__ void tc_prep_rev_body(const float* __restrict__ w, int K, int S, const DepthPack& dp,
+                                                 unsigned char* __restrict__ rimg, int per_block, int cta,
+                                                 double (*vr)[33], double (*vi)[33]) {
     constexpr int n = 5, N = 32;
-    __shared__ double vr[N][N + 1], vi[N][N + 1];
     const int j = threadIdx.x;
-    int s = blockIdx.x, k = 0, s0 = 0;
+    int s = cta, k = 0, s0 = 0;
     if (per_block) {
-        k = blockIdx.x;
+        k = cta;
         for (int kk = 0; kk < k; ++kk) s0 += dp.d[kk];
         s = s0;
     } else {
@@ -137,6 +137,14 @@ __global__ void __launch_bounds__(32) tc_prep_rev_kernel(const float* __restrict
         put(2 * i + 1, 2 * j, im);
         put(2 * i + 1, 2 * j + 1, re);
     }
+}
+// forward images (CTAs 0 .. K-1) and reverse images (the rest) in ONE launch: the two sets are independent
+__global__ void __launch_bounds__(32) tc_prep_all_kernel(const float* __restrict__ w, int K, int S, DepthPack dp,
+                                                         unsigned char* __restrict__ bimg, unsigned char* __restrict__ rimg,
+                                                         int per_block) {
+    __shared__ double vr[32][33], vi[32][33];
+    if ((int)blockIdx.x < K) tc_prep_body(w, K, dp, bimg, blockIdx.x, vr, vi);
+    else tc_prep_rev_body(w, K, S, dp, rimg, per_block, (int)blockIdx.x - K, vr, vi);
 }
 
 // ---------------------------------------------------------------------------------------------------------

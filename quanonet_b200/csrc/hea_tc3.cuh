@@ -82,7 +82,7 @@ __device__ __forceinline__ void tc_store_operand2(uint32_t taddr, unsigned char*
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// the reverse-sweep kernel.  images: K whole-block un-apply images in sweep order (tc_prep_rev_kernel, per_block);
+// the reverse-sweep kernel.  images: K whole-block un-apply images in sweep order (tc_prep_all_kernel, per_block);
 // state: the final state rows left by the forward-only kernel; acc: [2 gridDim.x slots][K][2048] floats (written, not
 // accumulated, in a slot's first round: no clearing needed)
 // ---------------------------------------------------------------------------------------------------------
@@ -352,7 +352,8 @@ hea_tc_rev_kernel(const HeaParams<float> p, const unsigned char* __restrict__ im
                 // is drained.  The slots' accumulators (2 x 148 x K x 8 KB = 142 MB at K = 60) cycle through L2 once per round
                 // and are re-fetched from HBM (ncu: 4.5 GB read + 4.0 GB written per 1M-sample step, 16 % of the HBM
                 // bandwidth over the kernel).  Tried and dropped: an L2 prefetch of block k-1's lines from here (4 % slower),
-                // evict_last / evict_first fractional L2 policies on these accesses (no change in traffic or time).
+                // evict_last / evict_first fractional L2 policies on these accesses (no change in traffic or time), issuing these
+                // loads before the operand split (no change).
                 float4* ak = reinterpret_cast<float4*>(acc + ((size_t)(blockIdx.x * NT + t) * p.K + k) * kTcAccLen) + quarter * 128 + lane;
                 float4 old4[4];
                 if (round > 0) {
@@ -447,7 +448,7 @@ hea_tc_rev_kernel(const HeaParams<float> p, const unsigned char* __restrict__ im
             // a barrier wait that timed out leaves garbage: poison this warp's partial sums so that the loss and
             // every gradient of the step read NaN instead of a plausible number
             if (lane == 0 && __ldcg(err) != 0) {
-                atomicAdd(mrow, __int_as_float(0x7fc00000));
+                atomicAdd(p.mpart, __int_as_float(0x7fc00000));      // row 0: the only row finalize reads for the moments
                 atomicAdd(srow + 1, __int_as_float(0x7fc00000));
             }
         }

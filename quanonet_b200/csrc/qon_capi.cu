@@ -186,7 +186,7 @@ __global__ void finalize_enc_kernel(const T* __restrict__ mpart, int rows, int64
 // ---------------------------------------------------------------------------------------------
 struct FlatLayout { int64_t w_off, fw_off, fb_off, sums_off, len; };
 
-__global__ void __launch_bounds__(256) finalize_exchange_kernel(const float* __restrict__ mpart, int rows, int64_t rowlen,
+__global__ void __launch_bounds__(256) finalize_exchange_kernel(const float* __restrict__ mpart, int rows_m, int rows, int64_t rowlen,
                                                                 int VP, int FVP, int n, int S, int K,
                                                                 const float* __restrict__ w, float* flat, FlatLayout fl,
                                                                 PeerPtrs pp, int world, int rank, int64_t max_len,
@@ -210,7 +210,7 @@ __global__ void __launch_bounds__(256) finalize_exchange_kernel(const float* __r
         const int RG = 256 / VP, slot = t % VP, rg = t / VP;
         double acc = 0.0;
         if (rg < RG)
-            for (int r = rg; r < rows; r += RG) acc += (double)mpart[(int64_t)r * rowlen + (int64_t)b * VP + slot];
+            for (int r = rg; r < rows_m; r += RG) acc += (double)mpart[(int64_t)r * rowlen + (int64_t)b * VP + slot];
         sm[t] = rg < RG ? acc : 0.0;
         __syncthreads();
         if (t < n) {
@@ -656,18 +656,28 @@ int run(const Job& j) {
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return fail((int)e, "prep launch failed: %s", cudaGetErrorString(e));
     }
+    // partial rows the finalize kernels have to sum: every row of the plan, unless the tensor-core tier ran — it fills
+    // one row per compute warp, and with the GEMM-form weight gradients (hea_tc3.cuh) the moments sit in row 0 alone
+    int rows_mom = j.B > 0 ? pl.rows : 0, rows_enc = rows_mom;
+    bool use_tc = false;
     if (j.B > 0) {
         cudaError_t e;
         const TcConfig& tcc = tc_config();
-        bool use_tc = false;
         if constexpr (sizeof(T) == 4)
             use_tc = tcc.enable && n == 5 && j.ham_kind == QON_HAM_DIAG && j.B >= tcc.min_batch;
         if (use_tc) {
             if constexpr (sizeof(T) == 4) {
                 int dev; DeviceInfo di;
                 if (!device_info(&dev, &di)) return fail(QON_ERR_NO_DEVICE, "no usable CUDA device");
-                e = tc_launch(mode, tcc.enable == 3 ? 3 : tcc.enable == 2 ? 2 : 4, di.sms, (const HeaParams<float>&)p, (const float*)j.w, dp,
+                const int version = tcc.enable == 3 ? 3 : tcc.enable == 2 ? 2 : 4;
+                e = tc_launch(mode, version, di.sms, (const HeaParams<float>&)p, (const float*)j.w, dp,
                               base + pl.off_tc, tcc.dbg, tcc.err, st);
+                if (j.grad) {
+                    int64_t tcg = (j.B + 255) / 256;
+                    if (tcg > di.sms) tcg = di.sms;
+                    rows_enc = (int)tcg * 8 < pl.rows ? (int)tcg * 8 : pl.rows;
+                    rows_mom = version == 4 ? 1 : rows_enc;
+                }
             } else e = cudaErrorInvalidValue;
         } else if (pl.fast_warp) {
             if constexpr (sizeof(T) == 4) e = warp_launch_f32(n, mode, pl.grid, pl.wp, (const HeaParams<float>&)p, dp, st);
@@ -693,9 +703,8 @@ int run(const Job& j) {
     }
     if (j.grad && j.flat) {
         if constexpr (sizeof(T) == 4) {
-            const int rows = j.B > 0 ? pl.rows : 0;
             finalize_exchange_kernel<<<pl.S + K + 1, 256, 0, st>>>(
-                (const float*)p.mpart, rows, pl.rowlen, pl.vp, pl.fvp, n, pl.S, K, (const float*)j.w, j.flat, j.fl, j.peers,
+                (const float*)p.mpart, rows_mom, rows_enc, pl.rowlen, pl.vp, pl.fvp, n, pl.S, K, (const float*)j.w, j.flat, j.fl, j.peers,
                 j.world, j.rank, j.peer_max_len, kPeerTimeoutCycles);
             cudaError_t e = cudaGetLastError();
             if (e != cudaSuccess) return fail((int)e, "finalize+exchange launch failed: %s", cudaGetErrorString(e));
@@ -703,16 +712,15 @@ int run(const Job& j) {
         return 0;
     }
     if (j.grad) {
-        const int rows = j.B > 0 ? pl.rows : 0;
         int threads = 256;
         while (threads < pl.vp) threads <<= 1;
         const int RG = threads / pl.vp;
         finalize_kernel<T><<<pl.S, threads, (size_t)RG * pl.vp * sizeof(double), st>>>(
-            p.mpart, rows, pl.rowlen, pl.vp, n, (const T*)j.w, (T*)j.grad_w);
+            p.mpart, rows_mom, pl.rowlen, pl.vp, n, (const T*)j.w, (T*)j.grad_w);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return fail((int)e, "finalize launch failed: %s", cudaGetErrorString(e));
         if (j.enc && (j.grad_fw || j.grad_fb || j.sums)) {
-            finalize_enc_kernel<T><<<K + 1, 256, 0, st>>>(p.mpart, rows, pl.rowlen, (int64_t)pl.S * pl.vp, pl.fvp, n, K,
+            finalize_enc_kernel<T><<<K + 1, 256, 0, st>>>(p.mpart, rows_enc, pl.rowlen, (int64_t)pl.S * pl.vp, pl.fvp, n, K,
                                                           (T*)j.grad_fw, (T*)j.grad_fb, (T*)j.sums);
             e = cudaGetLastError();
             if (e != cudaSuccess) return fail((int)e, "finalize_enc launch failed: %s", cudaGetErrorString(e));
