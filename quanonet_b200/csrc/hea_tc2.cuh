@@ -321,7 +321,13 @@ hea_tc_kernel(const HeaParams<float> p, const unsigned char* __restrict__ images
 
     const int lane = threadIdx.x & 31, warp = tc::warp_uniform(threadIdx.x >> 5);
     const int64_t ntiles = (p.B + 127) / 128;
-    const int64_t rounds = (ntiles + (int64_t)gridDim.x * NT - 1) / ((int64_t)gridDim.x * NT);
+    // Tile slot (CTA, t) takes tiles t * grid + CTA, + grid * NT, ...: a partial last round spreads over the CTAs one tile
+    // each (a lone tile has the SM to itself and runs faster than one of a pair), and a slot simply stops after its last
+    // live tile instead of idling through dead ones.
+    auto live_rounds = [&](int t) -> int64_t {
+        const int64_t first = (int64_t)t * gridDim.x + blockIdx.x, step = (int64_t)gridDim.x * NT;
+        return first < ntiles ? (ntiles - first + step - 1) / step : 0;
+    };
     const int nsteps = (GRAD && SPLIT ? 0 : p.K) + (GRAD ? p.S : 0);
 
     if (threadIdx.x == 0) {
@@ -349,7 +355,7 @@ hea_tc_kernel(const HeaParams<float> p, const unsigned char* __restrict__ images
             const uint32_t ring = tc::smem_u32(tc_smem + (size_t)t * NS * kTcImgBytes);
             const uint32_t bar_a_t = tc::smem_u32(&bar_a[t]), bar_d_t = tc::smem_u32(&bar_d[t]);
             constexpr uint32_t idesc = tc::idesc_f16(128, 64);
-            const int64_t total = rounds * nsteps;
+            const int64_t total = live_rounds(t) * nsteps;
             auto fetch = [&](int64_t g) {
                 const int stage = (int)(g % NS);
                 const uint32_t fb = tc::smem_u32(&bar_full[t][stage]);
@@ -429,8 +435,9 @@ hea_tc_kernel(const HeaParams<float> p, const unsigned char* __restrict__ images
             qm1[q] = ENC != 0 ? q % p.in1 : 0;
         }
 
+        const int64_t rounds = live_rounds(t);
         for (int64_t round = 0; round < rounds; ++round) {
-            const int64_t tile = (round * gridDim.x + blockIdx.x) * NT + t;
+            const int64_t tile = round * gridDim.x * NT + (int64_t)t * gridDim.x + blockIdx.x;
             const int64_t b = tile * 128 + quarter * 32 + lane;
             const bool valid = b < p.B;
             const int64_t bc = valid ? b : p.B - 1;

@@ -102,7 +102,13 @@ hea_tc_rev_kernel(const HeaParams<float> p, const unsigned char* __restrict__ im
 
     const int lane = threadIdx.x & 31, warp = tc::warp_uniform(threadIdx.x >> 5);
     const int64_t ntiles = (p.B + 127) / 128;
-    const int64_t rounds = (ntiles + (int64_t)gridDim.x * NT - 1) / ((int64_t)gridDim.x * NT);
+    // Tile slot (CTA, t) takes tiles t * grid + CTA, + grid * NT, ...: a partial last round spreads over the CTAs one tile
+    // each (a lone tile has the SM to itself and runs faster than one of a pair), and a slot simply stops after its last
+    // live tile instead of idling through dead ones.
+    auto live_rounds = [&](int t) -> int64_t {
+        const int64_t first = (int64_t)t * gridDim.x + blockIdx.x, step = (int64_t)gridDim.x * NT;
+        return first < ntiles ? (ntiles - first + step - 1) / step : 0;
+    };
 
     if (threadIdx.x == 0) {
         for (int t = 0; t < NT; ++t) {
@@ -138,7 +144,7 @@ hea_tc_rev_kernel(const HeaParams<float> p, const unsigned char* __restrict__ im
             // operand rows: groups of 8 samples 1024 B apart (the K direction of the outer product), groups of 8
             // components 128 B apart (its M / N direction)
             const uint32_t o_lbo = (flags & 2) ? 128u : 1024u, o_sbo = (flags & 2) ? 1024u : 128u;
-            const int64_t total = rounds * p.K;
+            const int64_t total = live_rounds(t) * p.K;
             auto fetch = [&](int64_t g) {
                 const int stage = (int)(g % NS);
                 const uint32_t fb = tc::smem_u32(&bar_full[t][stage]);
@@ -244,8 +250,15 @@ hea_tc_rev_kernel(const HeaParams<float> p, const unsigned char* __restrict__ im
             qm1[q] = ENC != 0 ? q % p.in1 : 0;
         }
 
+        const int64_t rounds = live_rounds(t);
+        if (rounds == 0) {       // a slot without a tile still owns accumulators the slot sums read
+            float4* az = reinterpret_cast<float4*>(acc + (size_t)(blockIdx.x * NT + t) * p.K * kTcAccLen) + quarter * 128 + lane;
+            for (int k = 0; k < p.K; ++k)
+#pragma unroll
+                for (int v = 0; v < 4; ++v) __stcg(az + (size_t)k * (kTcAccLen / 4) + 32 * v, make_float4(0.f, 0.f, 0.f, 0.f));
+        }
         for (int64_t round = 0; round < rounds; ++round) {
-            const int64_t tile = (round * gridDim.x + blockIdx.x) * NT + t;
+            const int64_t tile = round * gridDim.x * NT + (int64_t)t * gridDim.x + blockIdx.x;
             const int64_t b = tile * 128 + quarter * 32 + lane;
             const bool valid = b < p.B;
             const bool tile_live = tile * 128 < p.B;
