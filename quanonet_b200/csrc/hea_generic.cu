@@ -26,7 +26,7 @@ GenericPlan plan_t(int n, int mode) {
     gp.state_global = state > kSmemBudget;
     gp.smem_bytes = gp.state_global ? 0 : state;
     gp.threads = N >= 2048 ? 512 : (N >= 512 ? 256 : 128);
-    if (gp.state_global) gp.threads = 1024;
+    if (gp.state_global) gp.threads = 512;       // (the kernel is built for at most 512 threads: two-gate passes hold 8 amplitudes per thread)
     auto k = pick<T>(mode, gp.state_global);
     if (gp.smem_bytes > 48 * 1024)
         cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gp.smem_bytes);

@@ -57,6 +57,116 @@ __device__ __forceinline__ void g_apply(T* re, T* im, int64_t N, unsigned m, uns
     __syncthreads();
 }
 
+// Two gates on two different logical qubits in ONE pass over the state (half the shared-memory traffic and half the
+// barriers of two g_apply calls): the four states {e, e^m1, e^m2, e^m1^m2} form a closed group; its representative
+// has the two pivot bits of (m1, m2) cleared, e00 is the member whose two logical bits are 0.
+struct G2 {
+    int lo, hi;          // pivot bit positions, lo < hi
+    unsigned m1, m2;
+};
+__device__ __forceinline__ G2 g2_make(unsigned m1, unsigned m2) {
+    const int l1 = __ffs((int)m1) - 1;
+    const unsigned m2p = ((m2 >> l1) & 1u) ? (m2 ^ m1) : m2;      // same group, pivot of m1 cleared
+    const int l2 = __ffs((int)m2p) - 1;
+    G2 g;
+    g.lo = l1 < l2 ? l1 : l2;
+    g.hi = l1 < l2 ? l2 : l1;
+    g.m1 = m1;
+    g.m2 = m2;
+    return g;
+}
+__device__ __forceinline__ int64_t g2_rep(const G2& g, int64_t t) {
+    int64_t i = ((t >> g.lo) << (g.lo + 1)) | (t & (((int64_t)1 << g.lo) - 1));
+    return ((i >> g.hi) << (g.hi + 1)) | (i & (((int64_t)1 << g.hi) - 1));
+}
+template <typename T>
+__device__ __forceinline__ void gate2x2(T& x0r, T& x0i, T& x1r, T& x1i, T ar, T ai, T br, T bi) {
+    const T n0r = fma_(-bi, x1i, fma_(-br, x1r, fma_(-ai, x0i, ar * x0r)));
+    const T n0i = fma_(bi, x1r, fma_(-br, x1i, fma_(ai, x0r, ar * x0i)));
+    const T n1r = fma_(ai, x1i, fma_(ar, x1r, fma_(-bi, x0i, br * x0r)));
+    const T n1i = fma_(-ai, x1r, fma_(ar, x1i, fma_(bi, x0r, br * x0i)));
+    x0r = n0r; x0i = n0i; x1r = n1r; x1i = n1i;
+}
+// U^+ on a pair
+template <typename T>
+__device__ __forceinline__ void ungate2x2(T& p0r, T& p0i, T& p1r, T& p1i, T ar, T ai, T br, T bi) {
+    const T n0r = fma_(bi, p1i, fma_(br, p1r, fma_(ai, p0i, ar * p0r)));
+    const T n0i = fma_(-bi, p1r, fma_(br, p1i, fma_(-ai, p0r, ar * p0i)));
+    const T n1r = fma_(-ai, p1i, fma_(ar, p1r, fma_(bi, p0i, -br * p0r)));
+    const T n1i = fma_(ai, p1r, fma_(ar, p1i, fma_(-bi, p0r, -br * p0i)));
+    p0r = n0r; p0i = n0i; p1r = n1r; p1i = n1i;
+}
+template <typename T>
+__device__ __forceinline__ void g_apply2(T* re, T* im, int64_t N, unsigned m1, unsigned r1, unsigned m2, unsigned r2,
+                                         const T (&u1)[4], const T (&u2)[4]) {
+    const G2 g = g2_make(m1, m2);
+    const int64_t quarter = N >> 2;
+    for (int64_t t = threadIdx.x; t < quarter; t += blockDim.x) {
+        const int64_t i0 = g2_rep(g, t);
+        const int64_t e00 = i0 ^ ((__popc((unsigned)i0 & r1) & 1) ? (int64_t)m1 : 0) ^ ((__popc((unsigned)i0 & r2) & 1) ? (int64_t)m2 : 0);
+        const int64_t e10 = e00 ^ (int64_t)m1, e01 = e00 ^ (int64_t)m2, e11 = e10 ^ (int64_t)m2;
+        T ar0 = re[e00], ai0 = im[e00], ar1 = re[e10], ai1 = im[e10], ar2 = re[e01], ai2 = im[e01], ar3 = re[e11], ai3 = im[e11];
+        gate2x2(ar0, ai0, ar1, ai1, u1[0], u1[1], u1[2], u1[3]);      // qubit 1: (00, 10) and (01, 11)
+        gate2x2(ar2, ai2, ar3, ai3, u1[0], u1[1], u1[2], u1[3]);
+        gate2x2(ar0, ai0, ar2, ai2, u2[0], u2[1], u2[2], u2[3]);      // qubit 2: (00, 01) and (10, 11)
+        gate2x2(ar1, ai1, ar3, ai3, u2[0], u2[1], u2[2], u2[3]);
+        re[e00] = ar0; im[e00] = ai0; re[e10] = ar1; im[e10] = ai1;
+        re[e01] = ar2; im[e01] = ai2; re[e11] = ar3; im[e11] = ai3;
+    }
+    __syncthreads();
+}
+
+// moments of one pair, accumulated: x, y, z += Im <lam| {X, Y, Z} |psi> restricted to the pair
+template <typename T>
+__device__ __forceinline__ void pair_moments(T p0r, T p0i, T p1r, T p1i, T l0r, T l0i, T l1r, T l1i, T& x, T& y, T& z) {
+    x = fma_(l0r, p1i, x); x = fma_(-l0i, p1r, x); x = fma_(l1r, p0i, x); x = fma_(-l1i, p0r, x);
+    y = fma_(-l0r, p1r, y); y = fma_(-l0i, p1i, y); y = fma_(l1r, p0r, y); y = fma_(l1i, p0i, y);
+    z = fma_(l0r, p0i, z); z = fma_(-l0i, p0r, z); z = fma_(-l1r, p1i, z); z = fma_(l1i, p1r, z);
+}
+// reverse sweep for two logical qubits in one pass: moments of qubit 1, un-apply it on (psi, lam), moments of qubit 2 on
+// the result, un-apply it.  Per-warp partials: part1 / part2.
+template <typename T>
+__device__ __forceinline__ void g_bwd_group2(T* pr, T* pi, T* lr, T* li, int64_t N, unsigned m1, unsigned r1, unsigned m2,
+                                             unsigned r2, const T (&u1)[4], const T (&u2)[4], T (*part1)[3], T (*part2)[3]) {
+    const G2 g = g2_make(m1, m2);
+    const int64_t quarter = N >> 2;
+    T x1 = 0, y1 = 0, z1 = 0, x2 = 0, y2 = 0, z2 = 0;
+    for (int64_t t = threadIdx.x; t < quarter; t += blockDim.x) {
+        const int64_t i0 = g2_rep(g, t);
+        const int64_t e00 = i0 ^ ((__popc((unsigned)i0 & r1) & 1) ? (int64_t)m1 : 0) ^ ((__popc((unsigned)i0 & r2) & 1) ? (int64_t)m2 : 0);
+        const int64_t e[4] = {e00, e00 ^ (int64_t)m1, e00 ^ (int64_t)m2, e00 ^ (int64_t)m1 ^ (int64_t)m2};     // 00, 10, 01, 11
+        T P[4][2], L[4][2];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) { P[c][0] = pr[e[c]]; P[c][1] = pi[e[c]]; L[c][0] = lr[e[c]]; L[c][1] = li[e[c]]; }
+        pair_moments(P[0][0], P[0][1], P[1][0], P[1][1], L[0][0], L[0][1], L[1][0], L[1][1], x1, y1, z1);
+        pair_moments(P[2][0], P[2][1], P[3][0], P[3][1], L[2][0], L[2][1], L[3][0], L[3][1], x1, y1, z1);
+        ungate2x2(P[0][0], P[0][1], P[1][0], P[1][1], u1[0], u1[1], u1[2], u1[3]);
+        ungate2x2(P[2][0], P[2][1], P[3][0], P[3][1], u1[0], u1[1], u1[2], u1[3]);
+        ungate2x2(L[0][0], L[0][1], L[1][0], L[1][1], u1[0], u1[1], u1[2], u1[3]);
+        ungate2x2(L[2][0], L[2][1], L[3][0], L[3][1], u1[0], u1[1], u1[2], u1[3]);
+        pair_moments(P[0][0], P[0][1], P[2][0], P[2][1], L[0][0], L[0][1], L[2][0], L[2][1], x2, y2, z2);
+        pair_moments(P[1][0], P[1][1], P[3][0], P[3][1], L[1][0], L[1][1], L[3][0], L[3][1], x2, y2, z2);
+        ungate2x2(P[0][0], P[0][1], P[2][0], P[2][1], u2[0], u2[1], u2[2], u2[3]);
+        ungate2x2(P[1][0], P[1][1], P[3][0], P[3][1], u2[0], u2[1], u2[2], u2[3]);
+        ungate2x2(L[0][0], L[0][1], L[2][0], L[2][1], u2[0], u2[1], u2[2], u2[3]);
+        ungate2x2(L[1][0], L[1][1], L[3][0], L[3][1], u2[0], u2[1], u2[2], u2[3]);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) { pr[e[c]] = P[c][0]; pi[e[c]] = P[c][1]; lr[e[c]] = L[c][0]; li[e[c]] = L[c][1]; }
+    }
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) {
+        x1 += __shfl_xor_sync(0xffffffffu, x1, s); y1 += __shfl_xor_sync(0xffffffffu, y1, s); z1 += __shfl_xor_sync(0xffffffffu, z1, s);
+        x2 += __shfl_xor_sync(0xffffffffu, x2, s); y2 += __shfl_xor_sync(0xffffffffu, y2, s); z2 += __shfl_xor_sync(0xffffffffu, z2, s);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        T* a = part1[threadIdx.x >> 5];
+        T* b = part2[threadIdx.x >> 5];
+        a[0] = x1; a[1] = y1; a[2] = z1;
+        b[0] = x2; b[1] = y2; b[2] = z2;
+    }
+    __syncthreads();
+}
+
 template <typename T>
 __device__ __forceinline__ void fold_rx(const Vec4<T>& u, T theta, T& ar, T& ai, T& br, T& bi) {
     T sn, cs;
@@ -107,10 +217,10 @@ __device__ __forceinline__ void g_bwd_group(T* pr, T* pi, T* lr, T* li, int64_t 
 
 // STATE_GLOBAL: psi/lam slices in the HBM workspace instead of dynamic shared memory
 template <typename T, bool GRAD, bool NEED_GX, bool STATE_GLOBAL>
-__global__ void hea_generic_kernel(const HeaParams<T> p, const int n, const int VP, T* gstate) {
+__global__ void __launch_bounds__(512) hea_generic_kernel(const HeaParams<T> p, const int n, const int VP, T* gstate) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ T red[33];
-    __shared__ T part[2][32][3];          // per-warp moment partials, double-buffered by gate parity
+    __shared__ T part[4][32][3];          // per-warp moment partials: two gates per pass, double-buffered by pass parity
     __shared__ RingMap rm;
     const int64_t N = (int64_t)1 << n;
     const int nwarps = (blockDim.x + 31) >> 5;
@@ -131,11 +241,22 @@ __global__ void hea_generic_kernel(const HeaParams<T> p, const int n, const int 
         for (int k = 0; k < p.K; ++k) {
             const int d = p.depth[k];
             for (int j = 0; j < d; ++j, ++s) {
-                for (int q = 0; q < n; ++q) {
+                auto coef = [&](int q, T(&c)[4]) {
                     const Vec4<T> u = ldg4(p.ucoef + (int64_t)s * n + q);
-                    T ar = u.x, ai = u.y, br = u.z, bi = u.w;
-                    if (j == 0) fold_rx(u, xrow[(int64_t)k * n + q], ar, ai, br, bi);
-                    g_apply(pr, pi, N, rm.m[q], rm.r[q], ar, ai, br, bi);
+                    c[0] = u.x; c[1] = u.y; c[2] = u.z; c[3] = u.w;
+                    if (j == 0) fold_rx(u, xrow[(int64_t)k * n + q], c[0], c[1], c[2], c[3]);
+                };
+                int q = 0;
+                for (; q + 1 < n; q += 2) {          // two qubits per pass over the state
+                    T c1[4], c2[4];
+                    coef(q, c1);
+                    coef(q + 1, c2);
+                    g_apply2(pr, pi, N, rm.m[q], rm.r[q], rm.m[q + 1], rm.r[q + 1], c1, c2);
+                }
+                if (q < n) {
+                    T c1[4];
+                    coef(q, c1);
+                    g_apply(pr, pi, N, rm.m[q], rm.r[q], c1[0], c1[1], c1[2], c1[3]);
                 }
                 if (threadIdx.x == 0) ring_map_apply(rm, n, false);      // the ring relabels; the data stays
                 __syncthreads();
@@ -186,22 +307,37 @@ __global__ void hea_generic_kernel(const HeaParams<T> p, const int n, const int 
                     --s;
                     if (threadIdx.x == 0) ring_map_apply(rm, n, true);       // un-apply the ring: relabel back
                     __syncthreads();
-                    for (int q = n - 1; q >= 0; --q) {
+                    auto coef = [&](int q, T(&c)[4]) {
                         const Vec4<T> u = ldg4(p.ucoef + (int64_t)s * n + q);
-                        T ar = u.x, ai = u.y, br = u.z, bi = u.w;
-                        if (j == 0) fold_rx(u, xrow[(int64_t)k * n + q], ar, ai, br, bi);
-                        T (*pp)[3] = part[q & 1];
-                        g_bwd_group(pr, pi, lr, li, N, rm.m[q], rm.r[q], ar, ai, br, bi, pp);
-                        if (threadIdx.x == 0) {
-                            T mx = 0, my = 0, mz = 0;
-                            for (int w = 0; w < nwarps; ++w) { mx += pp[w][0]; my += pp[w][1]; mz += pp[w][2]; }   // fixed order
-                            T* m = mrow + (int64_t)s * VP + 3 * q;
-                            m[0] += mx; m[1] += my; m[2] += mz;      // row is private to this CTA
-                            if (NEED_GX && j == 0) {
-                                const Vec4<T> r = ldg4(p.rcoef + (int64_t)s * n + q);
-                                gxrow[(int64_t)k * n + q] = fma_(r.z, mz, fma_(r.y, my, r.x * mx));
-                            }
+                        c[0] = u.x; c[1] = u.y; c[2] = u.z; c[3] = u.w;
+                        if (j == 0) fold_rx(u, xrow[(int64_t)k * n + q], c[0], c[1], c[2], c[3]);
+                    };
+                    auto emit = [&](int q, T (*pp)[3]) {     // thread 0: per-warp partials -> this CTA's row, fixed order
+                        T mx = 0, my = 0, mz = 0;
+                        for (int w = 0; w < nwarps; ++w) { mx += pp[w][0]; my += pp[w][1]; mz += pp[w][2]; }
+                        T* m = mrow + (int64_t)s * VP + 3 * q;
+                        m[0] += mx; m[1] += my; m[2] += mz;      // row is private to this CTA
+                        if (NEED_GX && j == 0) {
+                            const Vec4<T> r = ldg4(p.rcoef + (int64_t)s * n + q);
+                            gxrow[(int64_t)k * n + q] = fma_(r.z, mz, fma_(r.y, my, r.x * mx));
                         }
+                    };
+                    int q = n - 1, pass = 0;
+                    for (; q >= 1; q -= 2, ++pass) {      // two qubits per pass over (psi, lam)
+                        T c1[4], c2[4];
+                        coef(q, c1);
+                        coef(q - 1, c2);
+                        T (*p1)[3] = part[2 * (pass & 1)];
+                        T (*p2)[3] = part[2 * (pass & 1) + 1];
+                        g_bwd_group2(pr, pi, lr, li, N, rm.m[q], rm.r[q], rm.m[q - 1], rm.r[q - 1], c1, c2, p1, p2);
+                        if (threadIdx.x == 0) { emit(q, p1); emit(q - 1, p2); }
+                    }
+                    if (q == 0) {
+                        T c1[4];
+                        coef(0, c1);
+                        T (*pp)[3] = part[2 * (pass & 1)];
+                        g_bwd_group(pr, pi, lr, li, N, rm.m[0], rm.r[0], c1[0], c1[1], c1[2], c1[3], pp);
+                        if (threadIdx.x == 0) emit(0, pp);
                     }
                 }
             }
