@@ -28,6 +28,10 @@ namespace qon {
 #ifndef QON_TC_SLOW_INLINE
 #define QON_TC_SLOW_INLINE 0      // experiment switch (scripts/build_tc_variant.sh): huge-angle sin/cos inlined instead of called
 #endif
+#ifndef QON_TC_REV_STAGES
+#define QON_TC_REV_STAGES 2       // experiment switch (scripts/build_tc_variant.sh): B-image ring stages per tile in the reverse kernel
+#endif
+
 constexpr int kTcImgBytes = 16384;             // per block: B_hi (8 KB) | B_lo (8 KB)
 constexpr float kTcSA = 32768.f;               // state scale  (|amplitude| <= 1 -> f16 normal range)
 constexpr float kTcSB = 1.f;                   // matrix scale: 1 keeps a GEMM's output at the operand scale (lo parts of

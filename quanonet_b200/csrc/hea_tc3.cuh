@@ -31,7 +31,7 @@
 namespace qon {
 
 struct TcRev {
-    static constexpr int NT = 2, NS = 2;
+    static constexpr int NT = 2, NS = QON_TC_REV_STAGES;
     static constexpr int COMPUTE_WARPS = 4 * NT, WARPS = COMPUTE_WARPS + 4, THREADS = WARPS * 32;
     static constexpr int TILE_COLS = 256;
     static constexpr int OPER_BYTES = 65536;                 // per tile: psi hi | psi lo | lam hi | lam lo, 16 KB each
@@ -151,9 +151,9 @@ hea_tc_rev_kernel(const HeaParams<float> p, const unsigned char* __restrict__ im
                 tc::mbar_expect_tx(fb, kTcImgBytes);
                 tc::bulk_g2s(ring + (uint32_t)stage * kTcImgBytes, images + (size_t)(g % p.K) * kTcImgBytes, kTcImgBytes, fb);
             };
-            for (int64_t g = 0; g < NS - 1 && g < total; ++g) fetch(g);
+            for (int64_t g = 0; g < (NS > 1 ? NS - 1 : 1) && g < total; ++g) fetch(g);
             bool dead = false;
-            uint32_t apar = 0, xpar = 0;
+            uint32_t apar = 0, xpar = 0, dpar_m = 0;
             auto gemm = [&](uint32_t d, uint32_t a, uint32_t sb) {      // D = A_hi B_hi + A_hi B_lo + A_lo B_hi
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
@@ -197,7 +197,15 @@ hea_tc_rev_kernel(const HeaParams<float> p, const unsigned char* __restrict__ im
                 tc::tc_fence_after();
                 if (!dead) outer();
                 tc::mma_commit(bar_g_t);
-                if (g + NS - 1 < total) fetch(g + NS - 1);
+                if constexpr (NS > 1) {
+                    if (g + NS - 1 < total) fetch(g + NS - 1);
+                } else {
+                    // one stage: the next image may land once both un-apply GEMMs have read this one (the compute warps
+                    // work on their results for far longer than the copy takes)
+                    if (!dead && !tc_wait(bar_d_t, dpar_m, err)) dead = true;
+                    dpar_m ^= 1u;
+                    if (g + 1 < total) fetch(g + 1);
+                }
             }
         }
         __syncwarp();
@@ -292,7 +300,7 @@ hea_tc_rev_kernel(const HeaParams<float> p, const unsigned char* __restrict__ im
                     for (int q = 0; q < NQ; ++q) {
                         int idx = base + (s0 ? qm0[q] : qm1[q]);
                         if (idx >= in) idx -= in;
-                        un[q] = __ldg(ur + idx);
+                        un[q] = __ldg(ur + idx);      // through L1: bypassing it (ld.global.nc.L1::no_allocate) measured 9.1 vs 7.9 ms per step
                     }
                 }
             };
