@@ -6,8 +6,10 @@
 
 namespace qon {
 
-static int tc_grad_grid(int64_t B, int sms) {
-    int64_t grid = ((B + 127) / 128 + 1) / 2;
+// One CTA per SM as soon as there are that many tiles: a tile slot without a tile costs nothing (it stops after its last
+// live tile), and a lone tile has the SM to itself — so a mid-size batch spreads over all SMs instead of filling a few.
+static int tc_grid(int64_t B, int sms) {
+    int64_t grid = (B + 127) / 128;
     if (grid > sms) grid = sms;
     return (int)(grid < 1 ? 1 : grid);
 }
@@ -16,7 +18,7 @@ size_t tc_workspace_bytes(int K, int S, int64_t B, int sms) {
     // operand images + flags (error word, max |g| bits) + (training step) one 256-byte state row per sample + the
     // outer-product accumulators of the GEMM-form weight gradients: one per (CTA, tile slot) and block, + their fp64 sums
     return (size_t)(K + S) * kTcImgBytes + 256 +
-           (B > 0 ? (size_t)B * 256 + (size_t)2 * tc_grad_grid(B, sms) * K * kTcAccLen * sizeof(float) +
+           (B > 0 ? (size_t)B * 256 + (size_t)2 * tc_grid(B, sms) * K * kTcAccLen * sizeof(float) +
                         (size_t)K * kTcAccLen * sizeof(double) : 0);
 }
 
@@ -70,11 +72,7 @@ cudaError_t tc_launch(int mode, int version, int sms, const HeaParams<float>& p,
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     const int64_t ntiles = (p.B + 127) / 128;
-    auto grid_for = [&](int nt) {
-        int64_t grid = (ntiles + nt - 1) / nt;
-        if (grid > sms) grid = sms;
-        return (int)(grid < 1 ? 1 : grid);
-    };
+    auto grid_for = [&](int) { return tc_grid(p.B, sms); };
     if (!grad) {
         const int g = grid_for(4);
         if (mode == 0) return dbg ? tc_launch_t<false, false, 0, true>(g, p, img, dbg, err, nullptr, st)
@@ -96,7 +94,8 @@ cudaError_t tc_launch(int mode, int version, int sms, const HeaParams<float>& p,
         }
         if (e != cudaSuccess) return e;
         double* ysum = reinterpret_cast<double*>(gacc + (size_t)2 * g * p.K * kTcAccLen);
-        tc_slot_reduce_kernel<<<p.K * 8, 256, 0, st>>>(gacc, 2 * g, p.K, ysum);
+        const int nslots = (int)(ntiles < 2 * (int64_t)g ? ntiles : 2 * (int64_t)g);      // slots with a tile: a prefix (slot = t * grid + CTA)
+        tc_slot_reduce_kernel<<<p.K * 8, 256, 0, st>>>(gacc, nslots, p.K, ysum);
         tc_moment_kernel<<<p.K, 1024, 0, st>>>(ysum, gmax, p.hdiag, w, p.K, dp, p.mpart);
         return cudaGetLastError();
     }

@@ -83,8 +83,9 @@ __device__ __forceinline__ void tc_store_operand2(uint32_t taddr, unsigned char*
 
 // ---------------------------------------------------------------------------------------------------------
 // the reverse-sweep kernel.  images: K whole-block un-apply images in sweep order (tc_prep_all_kernel, per_block);
-// state: the final state rows left by the forward-only kernel; acc: [2 gridDim.x slots][K][2048] floats (written, not
-// accumulated, in a slot's first round: no clearing needed)
+// state: the final state rows left by the forward-only kernel; acc: [2 gridDim.x slots][K][2048] floats, slot =
+// t * gridDim.x + CTA (written, not accumulated, in a slot's first round: no clearing needed; the slots that have a tile
+// are the first min(tiles, 2 gridDim.x))
 // ---------------------------------------------------------------------------------------------------------
 template <bool NEED_GX, int ENC>
 __global__ void __launch_bounds__(TcRev::THREADS, 1)
@@ -259,12 +260,6 @@ hea_tc_rev_kernel(const HeaParams<float> p, const unsigned char* __restrict__ im
         }
 
         const int64_t rounds = live_rounds(t);
-        if (rounds == 0) {       // a slot without a tile still owns accumulators the slot sums read
-            float4* az = reinterpret_cast<float4*>(acc + (size_t)(blockIdx.x * NT + t) * p.K * kTcAccLen) + quarter * 128 + lane;
-            for (int k = 0; k < p.K; ++k)
-#pragma unroll
-                for (int v = 0; v < 4; ++v) __stcg(az + (size_t)k * (kTcAccLen / 4) + 32 * v, make_float4(0.f, 0.f, 0.f, 0.f));
-        }
         for (int64_t round = 0; round < rounds; ++round) {
             const int64_t tile = round * gridDim.x * NT + (int64_t)t * gridDim.x + blockIdx.x;
             const int64_t b = tile * 128 + quarter * 32 + lane;
@@ -375,7 +370,7 @@ hea_tc_rev_kernel(const HeaParams<float> p, const unsigned char* __restrict__ im
                 // bandwidth over the kernel).  Tried and dropped: an L2 prefetch of block k-1's lines from here (4 % slower),
                 // evict_last / evict_first fractional L2 policies on these accesses (no change in traffic or time), issuing these
                 // loads before the operand split (no change).
-                float4* ak = reinterpret_cast<float4*>(acc + ((size_t)(blockIdx.x * NT + t) * p.K + k) * kTcAccLen) + quarter * 128 + lane;
+                float4* ak = reinterpret_cast<float4*>(acc + ((size_t)(t * gridDim.x + blockIdx.x) * p.K + k) * kTcAccLen) + quarter * 128 + lane;
                 float4 old4[4];
                 if (round > 0) {
 #pragma unroll

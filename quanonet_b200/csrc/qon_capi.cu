@@ -536,15 +536,11 @@ int make_plan(int64_t B, int n, int K, const int* depth, int dtype, int mode, Pl
         pl->fvp = 0;
     }
     if (dtype == QON_F32 && n == 5) {
-        // the tensor-core tier (hea_tc2.cuh) writes one partial row per compute warp: 8 warps x min(SMs, ceil(B / 256)) CTAs
-        // (2-tile layout) or 12 warps x min(SMs, ceil(B / 384)) CTAs (3-tile layout)
-        int64_t tcg = (B + 255) / 256, tcg3 = (B + 383) / 384;
+        // the tensor-core tier (hea_tc2.cuh, hea_tc3.cuh) writes one partial row per compute warp: 8 warps x min(SMs, tiles) CTAs
+        int64_t tcg = (B + 127) / 128;          // CTAs of the gradient kernels: one per SM once there are that many tiles
         if (tcg > di.sms) tcg = di.sms;
-        if (tcg3 > di.sms) tcg3 = di.sms;
         if (tcg < 1) tcg = 1;
-        if (tcg3 < 1) tcg3 = 1;
         if (pl->rows < (int)tcg * 8) pl->rows = (int)tcg * 8;
-        if (pl->rows < (int)tcg3 * 12) pl->rows = (int)tcg3 * 12;
     }
     size_t off = 0;
     pl->off_u = off; off = align_up(off + (size_t)S * n * 4 * es);
@@ -673,7 +669,7 @@ int run(const Job& j) {
                 e = tc_launch(mode, version, di.sms, (const HeaParams<float>&)p, (const float*)j.w, dp,
                               base + pl.off_tc, tcc.dbg, tcc.err, st);
                 if (j.grad) {
-                    int64_t tcg = (j.B + 255) / 256;
+                    int64_t tcg = (j.B + 127) / 128;
                     if (tcg > di.sms) tcg = di.sms;
                     rows_enc = (int)tcg * 8 < pl.rows ? (int)tcg * 8 : pl.rows;
                     rows_mom = version == 4 ? 1 : rows_enc;
