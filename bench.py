@@ -327,7 +327,7 @@ def run_b200(args):
     kern_ms = float(np.mean([a.elapsed_time(b) for a, b in kernel_events]))
     # the same kernel call on the FFMA2 register kernels (tensor-core tier switched off), for the A/B in the record
     from quanonet_b200.ops import tensor_tier
-    tc_on = bool(tensor_tier(None)) and B >= 12289 and not args.unfused
+    tc_on = bool(tensor_tier(None)) and B >= 5121 and not args.unfused
     ffma2_ms = None
     if tc_on and rank == 0 or (tc_on and world > 1):
         saved_fx = getattr(trainer, "_fused_exchange", False)
@@ -481,7 +481,7 @@ def run_b200(args):
                                   "tier on, the sample-independent sublayers run as split-f16 GEMMs on tcgen05 (executed tensor "
                                   "flops are not credited), so the fraction can approach or exceed 1" if tc_on else
                                   "ALGORITHMIC gate-by-gate flops (SURVEY §8d) over the FP32 CUDA-core peak")},
-            "tensor_tier": {"enabled": tc_on, "min_batch": 12289,
+            "tensor_tier": {"enabled": tc_on, "min_batch": 5121,
                             "ffma2_kernel_ms": ffma2_ms, "ffma2_samples_per_s": (B / (ffma2_ms * 1e-3)) if ffma2_ms else None},
             "per_step": trace,
             "forward_only": {"value": B / (fwd_ms * 1e-3), "unit": "samples/s",

@@ -193,7 +193,7 @@ int qon_encoded_mse_step_dp(const void* u0, int64_t ldu0, int in0, int K0, const
  *   enable     1 = on, 0 = off (the FFMA2 register kernels serve every batch), -1 = leave unchanged;
  *              2 / 3 = on, with the earlier formulations of the gradient step (per-sublayer Pauli-string moments in
  *              two kernels / in one kernel), kept for A/B measurements
- *   min_batch  smallest batch routed to the tier (default 12289); < 0 = leave unchanged
+ *   min_batch  smallest batch routed to the tier (default 5121); < 0 = leave unchanged
  *   debug_state / error_flag: device pointers for kernel bring-up (state dump of the first tile; protocol
  *   time-out flag), NULL in production — a time-out poisons the outputs with NaN, it never hangs.
  * Process-wide; returns the previous `enable`. */

@@ -37,7 +37,7 @@ TcConfig& tc_config() {
     static TcConfig c = [] {
         const char* e = getenv("QON_TC");
         const char* m = getenv("QON_TC_MIN_B");
-        return TcConfig{e ? atoi(e) : 1, nullptr, nullptr, m ? (int64_t)atoll(m) : (int64_t)12289};   // right above the latency tier (12,288)
+        return TcConfig{e ? atoi(e) : 1, nullptr, nullptr, m ? (int64_t)atoll(m) : (int64_t)5121};   // measured crossover with the latency tier: ~4,100-5,000 samples in every mode (scripts/tc_modes.py, tc_ab.py)
     }();
     return c;
 }

@@ -40,5 +40,5 @@ for tier in tiers:
     rel = float(np.linalg.norm(vec - ref) / np.linalg.norm(ref))
     out[tier] = dict(ms=ms, samples_per_s=B / ms * 1e3, rel_vs_first=rel, err=int(err.item()))
     print(f"tier {tier}: {ms:.3f} ms  {B / ms * 1e3:.3e} samples/s  rel vs tier {tiers[0]}: {rel:.2e}  err {int(err.item())}", flush=True)
-lib.qon_tensor_tier(1, 12289, None, None)
+lib.qon_tensor_tier(1, 5121, None, None)
 json.dump(out, open(os.path.join(ROOT, "gpurun_out", "tc_ab.json"), "w"))

@@ -43,4 +43,4 @@ timed("grad w (mode 2), angles given", lambda: _backward_impl(gout, x, w, n, dep
 timed("grad w + dL/dx (mode 1), angles given", lambda: _backward_impl(gout, x, w, n, depths, None, 0, 0.0, 1.0, 0, True))
 timed("fused encoding + MSE + frequency-layer gradients (mode 5)",
       lambda: encoded_mse_step(trunk, branch, fw, fb, td, w, y, bias, 2.0 / B, n, depths, None, 0, 0.0, 1.0, 0, True))
-lib.qon_tensor_tier(1, 12289, None, None)
+lib.qon_tensor_tier(1, 5121, None, None)

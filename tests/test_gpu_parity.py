@@ -745,7 +745,7 @@ def tensor_tier_forced():
     lib = _lib.load()
     prev = tensor_tier(True, 0)
     yield
-    lib.qon_tensor_tier(int(prev), 12289, None, None)
+    lib.qon_tensor_tier(int(prev), 5121, None, None)
 
 
 def test_tensor_tier_golden_circuit_cases(cuda_device, tensor_tier_forced):
@@ -781,14 +781,14 @@ def test_tensor_tier_vs_oracle_and_register_kernels(cuda_device, depths):
     prev = tensor_tier(None)
     try:
         for tier in (True, False):
-            tensor_tier(tier, 0 if tier else 12289)
+            tensor_tier(tier, 0 if tier else 5121)
             f = hea_expval(t(x), t(w), n, depths, t(diag), 0, 0.0, 0.0, 0)
             o, gx, gw = hea_expval_backward(t(g), t(x), t(w), n, depths, t(diag), 0, 0.0, 0.0, 0, True)
             _, _, gw2 = hea_expval_backward(t(g), t(x), t(w), n, depths, t(diag), 0, 0.0, 0.0, 0, False)
             _, gxp, gwp = hea_expval_backward(t(g[:nref]), t(x[:nref]), t(w), n, depths, t(diag), 0, 0.0, 0.0, 0, True)
             res[tier] = [a.double().cpu().numpy() for a in (f[:, 0], o[:, 0], gx, gw, gw2, gxp, gwp)]
     finally:
-        _lib.load().qon_tensor_tier(int(prev), 12289, None, None)
+        _lib.load().qon_tensor_tier(int(prev), 5121, None, None)
     e_ref, gx_ref, gw_ref = orc.hea_forward_backward(x[:nref].astype(np.float64), w.astype(np.float64), n,
                                                      [(n, d) for d in depths], orc.ham_from_diag(diag, n), g[:nref].astype(np.float64))
     f, o, gx, gw, gw2, gxp, gwp = res[True]
@@ -831,13 +831,13 @@ def test_bench_config_fused_training_step_vs_oracle(cuda_device, tier):
     (b64, t64, y64), (branch, trunk, y) = _tiled_training_batch(320, 5, cuda_device)      # B = 20,480
     prev = tensor_tier(None)
     try:
-        tensor_tier(tier == "tensor", 0 if tier == "tensor" else 12289)
+        tensor_tier(tier == "tensor", 0 if tier == "tensor" else 5121)
         tr = DataParallelTrainer(model, lr=1e-3, optimizer="sgd")
         assert tr.fused_encoding
         loss = float(tr.compute_grads((branch, trunk), y))
         torch.cuda.synchronize()
     finally:
-        _lib.load().qon_tensor_tier(int(prev), 12289, None, None)
+        _lib.load().qon_tensor_tier(int(prev), 5121, None, None)
     params = {k: v.detach().double().cpu().numpy() for k, v in model.state_dict().items()}
     q = model.quantum_layer
     blocks, ham = q.block_configs, orc.ham_from_bound(n)
@@ -953,7 +953,7 @@ def test_tensor_tier_fused_encoding_modes(cuda_device, tf, kind):
     prev = tensor_tier(None)
     try:
         for tier in (True, False):
-            tensor_tier(tier, 0 if tier else 12289)
+            tensor_tier(tier, 0 if tier else 5121)
             for fused in (True, False):
                 m = mk().to(dev)
                 m.load_state_dict(m0.state_dict())
@@ -964,7 +964,7 @@ def test_tensor_tier_fused_encoding_modes(cuda_device, tf, kind):
                 torch.cuda.synchronize()
                 res[(tier, fused)] = (loss, tr.flat_grad.double().cpu().numpy().copy(), pred.double().cpu().numpy())
     finally:
-        _lib.load().qon_tensor_tier(int(prev), 12289, None, None)
+        _lib.load().qon_tensor_tier(int(prev), 5121, None, None)
     ref = res[(False, True)]
     for key in ((True, True), (True, False)):
         loss, grad, pred = res[key]
@@ -1068,7 +1068,7 @@ def test_tensor_tier_gemm_gradients_vs_oracle_ragged_batches(cuda_device, B):
         o, gx, gw = _tc_backward(lib, 1, g, x, w, depths, cuda_device, need_gx=True)
         o2, gx2, gw2 = _tc_backward(lib, 1, g, x, w, depths, cuda_device, need_gx=True)
     finally:
-        lib.qon_tensor_tier(1, 12289, None, None)
+        lib.qon_tensor_tier(1, 5121, None, None)
     # slot-private accumulators added in a fixed order (B = 40,000: two rounds per slot): bit-reproducible
     assert np.array_equal(gw, gw2) and np.array_equal(gx, gx2) and np.array_equal(o, o2)
     nref = min(B, 400)
@@ -1080,11 +1080,11 @@ def test_tensor_tier_gemm_gradients_vs_oracle_ragged_batches(cuda_device, B):
     else:       # full batch: against the FFMA2 register kernels
         from quanonet_b200.ops import hea_expval_backward
         t = lambda a: torch.tensor(a, dtype=torch.float32, device=cuda_device)
-        lib.qon_tensor_tier(0, 12289, None, None)
+        lib.qon_tensor_tier(0, 5121, None, None)
         try:
             _, _, gw_r = hea_expval_backward(t(g), t(x), t(w), n, depths, None, 0, 0.0, 1.0, 0, False)
         finally:
-            lib.qon_tensor_tier(1, 12289, None, None)
+            lib.qon_tensor_tier(1, 5121, None, None)
         assert rel_l2(gw, gw_r.double().cpu().numpy()) < 2 * TOL_F32
 
 
@@ -1103,7 +1103,7 @@ def test_tensor_tier_gemm_gradients_upstream_gradient_range(cuda_device, scale):
         o1, gx1, gw1 = _tc_backward(lib, 1, g, x, w, depths, cuda_device, need_gx=True)
         o0, gx0, gw0 = _tc_backward(lib, 0, g, x, w, depths, cuda_device, need_gx=True)       # FFMA2 register kernels
     finally:
-        lib.qon_tensor_tier(1, 12289, None, None)
+        lib.qon_tensor_tier(1, 5121, None, None)
     assert np.isfinite(gw1).all() and np.isfinite(gx1).all()
     assert rel_l2(gw1, gw0) < 2 * TOL_F32 and rel_l2(gx1, gx0) < 2 * TOL_F32 and rel_l2(o1, o0) < 2 * TOL_F32
 
@@ -1123,7 +1123,7 @@ def test_tensor_tier_gemm_gradients_zero_and_nan_upstream(cuda_device):
         _, _, gwn = _tc_backward(lib, 1, g, x, w, depths, cuda_device)
         assert np.isnan(gwn).all()
     finally:
-        lib.qon_tensor_tier(1, 12289, None, None)
+        lib.qon_tensor_tier(1, 5121, None, None)
 
 
 def test_tensor_tier_training_step_versions_agree(cuda_device):
@@ -1138,7 +1138,7 @@ def test_tensor_tier_training_step_versions_agree(cuda_device):
     try:
         res = {v: _tc_backward(lib, v, g, x, w, depths, cuda_device, need_gx=True) for v in (1, 2, 3)}
     finally:
-        lib.qon_tensor_tier(1, 12289, None, None)
+        lib.qon_tensor_tier(1, 5121, None, None)
     for v in (2, 3):
         for a, b in zip(res[1], res[v]):
             assert rel_l2(a, b) < TOL_F32, v
