@@ -52,7 +52,8 @@ __host__ __device__ constexpr int tc_b_offset(int nn, int kk) {
 // stored as Bt[nn = 2i + c'][kk = 2j + c] (K-major).
 // ---------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void tc_prep_body(const float* __restrict__ w, int K, const DepthPack& dp,
-                                             unsigned char* __restrict__ bimg, int k, double (*vr)[33], double (*vi)[33]) {
+                                             unsigned char* __restrict__ bimg, int k, double (*vr)[33], double (*vi)[33],
+                                             double (*uu)[4]) {
     constexpr int n = 5, N = 32;
     const int j = threadIdx.x;
     int s0 = 0;
@@ -64,17 +65,23 @@ __device__ __forceinline__ void tc_prep_body(const float* __restrict__ w, int K,
         vi[z][j] = 0.0;
     }
     for (int s = s0; s < s0 + d; ++s) {
-        for (int q = 0; q < n; ++q) {
-            const double a = (double)w[((int64_t)s * 3 + 0) * n + q];
-            const double b = (double)w[((int64_t)s * 3 + 1) * n + q];
-            const double c = (double)w[((int64_t)s * 3 + 2) * n + q];
+        // the sublayer's five fused rotations U = RY(c) RZ(b) RY(a) = [[al, -conj(be)], [be, conj(al)]]: lane q computes
+        // U[s, q] once (fp64 sin/cos), every lane reads it
+        __syncwarp();
+        if (j < n) {
+            const double a = (double)w[((int64_t)s * 3 + 0) * n + j];
+            const double b = (double)w[((int64_t)s * 3 + 1) * n + j];
+            const double c = (double)w[((int64_t)s * 3 + 2) * n + j];
             double sa, ca, sb, cb, sc, cc;
             sincos(0.5 * a, &sa, &ca);
             sincos(0.5 * b, &sb, &cb);
             sincos(0.5 * c, &sc, &cc);
-            // U = RY(c) RZ(b) RY(a) = [[al, -conj(be)], [be, conj(al)]]
-            const double ar = cb * (cc * ca - sc * sa), ai = -sb * (cc * ca + sc * sa);
-            const double br = cb * (sc * ca + cc * sa), bi = sb * (cc * sa - sc * ca);
+            uu[j][0] = cb * (cc * ca - sc * sa); uu[j][1] = -sb * (cc * ca + sc * sa);
+            uu[j][2] = cb * (sc * ca + cc * sa); uu[j][3] = sb * (cc * sa - sc * ca);
+        }
+        __syncwarp();
+        for (int q = 0; q < n; ++q) {
+            const double ar = uu[q][0], ai = uu[q][1], br = uu[q][2], bi = uu[q][3];
             for (int z = 0; z < N; ++z) {
                 if (z & (1 << q)) continue;
                 const int z1 = z | (1 << q);
@@ -127,8 +134,8 @@ __device__ __forceinline__ void tc_prep_body(const float* __restrict__ w, int K,
 }
 __global__ void __launch_bounds__(32) tc_prep_kernel(const float* __restrict__ w, int K, DepthPack dp,
                                                      unsigned char* __restrict__ bimg) {
-    __shared__ double vr[32][33], vi[32][33];
-    tc_prep_body(w, K, dp, bimg, blockIdx.x, vr, vi);
+    __shared__ double vr[32][33], vi[32][33], uu[5][4];
+    tc_prep_body(w, K, dp, bimg, blockIdx.x, vr, vi, uu);
 }
 
 // ---------------------------------------------------------------------------------------------------------

@@ -61,7 +61,7 @@ __device__ __forceinline__ u64 tc_pair(const uint32_t (&r)[64], int z) {
 // per_block (hea_tc3.cuh): grid = K CTAs, image K-1-k = the whole-block un-apply matrix C_{s0(k)} = M_k^+.
 __device__ __forceinline__ void tc_prep_rev_body(const float* __restrict__ w, int K, int S, const DepthPack& dp,
                                                  unsigned char* __restrict__ rimg, int per_block, int cta,
-                                                 double (*vr)[33], double (*vi)[33]) {
+                                                 double (*vr)[33], double (*vi)[33], double (*uu)[4]) {
     constexpr int n = 5, N = 32;
     const int j = threadIdx.x;
     int s = cta, k = 0, s0 = 0;
@@ -97,16 +97,21 @@ __device__ __forceinline__ void tc_prep_rev_body(const float* __restrict__ w, in
                 }
             }
         }
-        for (int q = 0; q < n; ++q) {
-            const double a = (double)w[((int64_t)ss * 3 + 0) * n + q];
-            const double b = (double)w[((int64_t)ss * 3 + 1) * n + q];
-            const double c = (double)w[((int64_t)ss * 3 + 2) * n + q];
+        __syncwarp();
+        if (j < n) {      // lane q computes U[ss, q] once
+            const double a = (double)w[((int64_t)ss * 3 + 0) * n + j];
+            const double b = (double)w[((int64_t)ss * 3 + 1) * n + j];
+            const double c = (double)w[((int64_t)ss * 3 + 2) * n + j];
             double sa, ca, sb, cb, sc, cc;
             sincos(0.5 * a, &sa, &ca);
             sincos(0.5 * b, &sb, &cb);
             sincos(0.5 * c, &sc, &cc);
-            const double ar = cb * (cc * ca - sc * sa), ai = -sb * (cc * ca + sc * sa);
-            const double br = cb * (sc * ca + cc * sa), bi = sb * (cc * sa - sc * ca);
+            uu[j][0] = cb * (cc * ca - sc * sa); uu[j][1] = -sb * (cc * ca + sc * sa);
+            uu[j][2] = cb * (sc * ca + cc * sa); uu[j][3] = sb * (cc * sa - sc * ca);
+        }
+        __syncwarp();
+        for (int q = 0; q < n; ++q) {
+            const double ar = uu[q][0], ai = uu[q][1], br = uu[q][2], bi = uu[q][3];
             // U^+ = [[conj(al), conj(be)], [-be, al]]
             for (int z = 0; z < N; ++z) {
                 if (z & (1 << q)) continue;
@@ -142,9 +147,9 @@ __device__ __forceinline__ void tc_prep_rev_body(const float* __restrict__ w, in
 __global__ void __launch_bounds__(32) tc_prep_all_kernel(const float* __restrict__ w, int K, int S, DepthPack dp,
                                                          unsigned char* __restrict__ bimg, unsigned char* __restrict__ rimg,
                                                          int per_block) {
-    __shared__ double vr[32][33], vi[32][33];
-    if ((int)blockIdx.x < K) tc_prep_body(w, K, dp, bimg, blockIdx.x, vr, vi);
-    else tc_prep_rev_body(w, K, S, dp, rimg, per_block, (int)blockIdx.x - K, vr, vi);
+    __shared__ double vr[32][33], vi[32][33], uu[5][4];
+    if ((int)blockIdx.x < K) tc_prep_body(w, K, dp, bimg, blockIdx.x, vr, vi, uu);
+    else tc_prep_rev_body(w, K, S, dp, rimg, per_block, (int)blockIdx.x - K, vr, vi, uu);
 }
 
 // ---------------------------------------------------------------------------------------------------------
