@@ -67,8 +67,8 @@ cudaError_t tc_launch(int mode, int version, int sms, const HeaParams<float>& p,
     const bool outer = grad && version == 4;
     cudaError_t e = cudaMemsetAsync(flag_block, 0, 256, st);      // (a caller-provided error word is the caller's to clear)
     if (e != cudaSuccess) return e;
-    if (grad) tc_prep_all_kernel<<<p.K + (outer ? p.K : p.S), 32, 0, st>>>(w, p.K, p.S, dp, img, img + (size_t)p.K * kTcImgBytes, outer ? 1 : 0);
-    else tc_prep_kernel<<<p.K, 32, 0, st>>>(w, p.K, dp, img);
+    if (grad) tc_prep_all_kernel<<<p.K + (outer ? p.K : p.S), 512, 0, st>>>(w, p.K, p.S, dp, img, img + (size_t)p.K * kTcImgBytes, outer ? 1 : 0);
+    else tc_prep_kernel<<<p.K, 512, 0, st>>>(w, p.K, dp, img);
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     const int64_t ntiles = (p.B + 127) / 128;

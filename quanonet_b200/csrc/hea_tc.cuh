@@ -44,8 +44,8 @@ __host__ __device__ constexpr int tc_b_offset(int nn, int kk) {
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// prep: block matrices in fp64 -> f16 hi/lo shared-memory images.  grid = K CTAs of 32 threads; thread j
-// pushes basis column j through the block.
+// prep: block matrices in fp64 -> f16 hi/lo shared-memory images.  grid = K CTAs of 512 threads: lane j owns basis
+// column j, warp pi one of the 16 row pairs of a gate (a barrier between gates).
 //   M_k = [H] W_k H,  W_k = prod_{sublayers} Ring * (x)_q U[s,q]   (leading H dropped for the last block)
 // Real form consumed by the GEMM (row vector x B):  out[2i + c'] = sum_{j,c} in[2j + c] * B[2j + c][2i + c'],
 //   B[2j][2i] = Re M_ij, B[2j+1][2i] = -Im M_ij, B[2j][2i+1] = Im M_ij, B[2j+1][2i+1] = Re M_ij,
@@ -55,20 +55,21 @@ __device__ __forceinline__ void tc_prep_body(const float* __restrict__ w, int K,
                                              unsigned char* __restrict__ bimg, int k, double (*vr)[33], double (*vi)[33],
                                              double (*uu)[4]) {
     constexpr int n = 5, N = 32;
-    const int j = threadIdx.x;
+    const int j = threadIdx.x & 31, pi = threadIdx.x >> 5;      // lane = basis column, warp = one of the 16 row pairs of a gate
     int s0 = 0;
     for (int kk = 0; kk < k; ++kk) s0 += dp.d[kk];
     const int d = dp.d[k];
     const double r = 0.17677669529663688110;   // 1 / sqrt(32)
-    for (int z = 0; z < N; ++z) {
+    for (int z = pi; z < N; z += 16) {
         vr[z][j] = (__popc(z & j) & 1) ? -r : r;
         vi[z][j] = 0.0;
     }
+    __syncthreads();
     for (int s = s0; s < s0 + d; ++s) {
         // the sublayer's five fused rotations U = RY(c) RZ(b) RY(a) = [[al, -conj(be)], [be, conj(al)]]: lane q computes
         // U[s, q] once (fp64 sin/cos), every lane reads it
-        __syncwarp();
-        if (j < n) {
+        __syncthreads();
+        if (pi == 0 && j < n) {
             const double a = (double)w[((int64_t)s * 3 + 0) * n + j];
             const double b = (double)w[((int64_t)s * 3 + 1) * n + j];
             const double c = (double)w[((int64_t)s * 3 + 2) * n + j];
@@ -79,40 +80,36 @@ __device__ __forceinline__ void tc_prep_body(const float* __restrict__ w, int K,
             uu[j][0] = cb * (cc * ca - sc * sa); uu[j][1] = -sb * (cc * ca + sc * sa);
             uu[j][2] = cb * (sc * ca + cc * sa); uu[j][3] = sb * (cc * sa - sc * ca);
         }
-        __syncwarp();
+        __syncthreads();
         for (int q = 0; q < n; ++q) {
             const double ar = uu[q][0], ai = uu[q][1], br = uu[q][2], bi = uu[q][3];
-            for (int z = 0; z < N; ++z) {
-                if (z & (1 << q)) continue;
-                const int z1 = z | (1 << q);
-                const double x0r = vr[z][j], x0i = vi[z][j], x1r = vr[z1][j], x1i = vi[z1][j];
-                vr[z][j] = ar * x0r - ai * x0i - br * x1r - bi * x1i;
-                vi[z][j] = ar * x0i + ai * x0r - br * x1i + bi * x1r;
-                vr[z1][j] = br * x0r - bi * x0i + ar * x1r + ai * x1i;
-                vi[z1][j] = br * x0i + bi * x0r + ar * x1i - ai * x1r;
-            }
+            const int z = ((pi >> q) << (q + 1)) | (pi & ((1 << q) - 1)), z1 = z | (1 << q);
+            const double x0r = vr[z][j], x0i = vi[z][j], x1r = vr[z1][j], x1i = vi[z1][j];
+            vr[z][j] = ar * x0r - ai * x0i - br * x1r - bi * x1i;
+            vi[z][j] = ar * x0i + ai * x0r - br * x1i + bi * x1r;
+            vr[z1][j] = br * x0r - bi * x0i + ar * x1r + ai * x1i;
+            vi[z1][j] = br * x0i + bi * x0r + ar * x1i - ai * x1r;
+            __syncthreads();
         }
         for (int i = 0; i < n; ++i) {   // CNOT ring: control (i+1)%n -> target i, i ascending
             const int c = (i + 1) % n;
-            for (int z = 0; z < N; ++z) {
-                if (((z >> c) & 1) && !((z >> i) & 1)) {
-                    const int z1 = z | (1 << i);
-                    double t = vr[z][j]; vr[z][j] = vr[z1][j]; vr[z1][j] = t;
-                    t = vi[z][j]; vi[z][j] = vi[z1][j]; vi[z1][j] = t;
-                }
+            const int z = ((pi >> i) << (i + 1)) | (pi & ((1 << i) - 1)), z1 = z | (1 << i);
+            if ((z >> c) & 1) {
+                double t = vr[z][j]; vr[z][j] = vr[z1][j]; vr[z1][j] = t;
+                t = vi[z][j]; vi[z][j] = vi[z1][j]; vi[z1][j] = t;
             }
+            __syncthreads();
         }
     }
     if (k < K - 1) {   // back to the Hadamard basis for the next block's diagonal encoding layer
         const double h = 0.70710678118654752440;
-        for (int q = 0; q < n; ++q)
-            for (int z = 0; z < N; ++z) {
-                if (z & (1 << q)) continue;
-                const int z1 = z | (1 << q);
-                const double x0r = vr[z][j], x0i = vi[z][j], x1r = vr[z1][j], x1i = vi[z1][j];
-                vr[z][j] = h * (x0r + x1r); vi[z][j] = h * (x0i + x1i);
-                vr[z1][j] = h * (x0r - x1r); vi[z1][j] = h * (x0i - x1i);
-            }
+        for (int q = 0; q < n; ++q) {
+            const int z = ((pi >> q) << (q + 1)) | (pi & ((1 << q) - 1)), z1 = z | (1 << q);
+            const double x0r = vr[z][j], x0i = vi[z][j], x1r = vr[z1][j], x1i = vi[z1][j];
+            vr[z][j] = h * (x0r + x1r); vi[z][j] = h * (x0i + x1i);
+            vr[z1][j] = h * (x0r - x1r); vi[z1][j] = h * (x0i - x1i);
+            __syncthreads();
+        }
     }
     __half* hi = reinterpret_cast<__half*>(bimg + (size_t)k * kTcImgBytes);
     __half* lo = hi + 4096;
@@ -124,7 +121,7 @@ __device__ __forceinline__ void tc_prep_body(const float* __restrict__ w, int K,
         hi[o] = h;
         lo[o] = l;
     };
-    for (int i = 0; i < N; ++i) {
+    for (int i = pi; i < N; i += 16) {
         const double re = vr[i][j], im = vi[i][j];
         put(2 * i, 2 * j, re);
         put(2 * i, 2 * j + 1, -im);
@@ -132,7 +129,7 @@ __device__ __forceinline__ void tc_prep_body(const float* __restrict__ w, int K,
         put(2 * i + 1, 2 * j + 1, re);
     }
 }
-__global__ void __launch_bounds__(32) tc_prep_kernel(const float* __restrict__ w, int K, DepthPack dp,
+__global__ void __launch_bounds__(512) tc_prep_kernel(const float* __restrict__ w, int K, DepthPack dp,
                                                      unsigned char* __restrict__ bimg) {
     __shared__ double vr[32][33], vi[32][33], uu[5][4];
     tc_prep_body(w, K, dp, bimg, blockIdx.x, vr, vi, uu);

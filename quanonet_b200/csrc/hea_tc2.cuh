@@ -63,7 +63,7 @@ __device__ __forceinline__ void tc_prep_rev_body(const float* __restrict__ w, in
                                                  unsigned char* __restrict__ rimg, int per_block, int cta,
                                                  double (*vr)[33], double (*vi)[33], double (*uu)[4]) {
     constexpr int n = 5, N = 32;
-    const int j = threadIdx.x;
+    const int j = threadIdx.x & 31, pi = threadIdx.x >> 5;      // lane = basis column, warp = one of the 16 row pairs of a gate
     int s = cta, k = 0, s0 = 0;
     if (per_block) {
         k = cta;
@@ -75,30 +75,28 @@ __device__ __forceinline__ void tc_prep_rev_body(const float* __restrict__ w, in
     const bool input_had = k < K - 1;   // the operand is the block's OUTPUT cut, held in the Hadamard basis except for the last block
     const double h = 0.70710678118654752440;
     auto fwht = [&]() {
-        for (int q = 0; q < n; ++q)
-            for (int z = 0; z < N; ++z) {
-                if (z & (1 << q)) continue;
-                const int z1 = z | (1 << q);
-                const double x0r = vr[z][j], x0i = vi[z][j], x1r = vr[z1][j], x1i = vi[z1][j];
-                vr[z][j] = h * (x0r + x1r); vi[z][j] = h * (x0i + x1i);
-                vr[z1][j] = h * (x0r - x1r); vi[z1][j] = h * (x0i - x1i);
-            }
+        for (int q = 0; q < n; ++q) {
+            const int z = ((pi >> q) << (q + 1)) | (pi & ((1 << q) - 1)), z1 = z | (1 << q);
+            const double x0r = vr[z][j], x0i = vi[z][j], x1r = vr[z1][j], x1i = vi[z1][j];
+            vr[z][j] = h * (x0r + x1r); vi[z][j] = h * (x0i + x1i);
+            vr[z1][j] = h * (x0r - x1r); vi[z1][j] = h * (x0i - x1i);
+            __syncthreads();
+        }
     };
-    for (int z = 0; z < N; ++z) { vr[z][j] = z == j ? 1.0 : 0.0; vi[z][j] = 0.0; }
+    for (int z = pi; z < N; z += 16) { vr[z][j] = z == j ? 1.0 : 0.0; vi[z][j] = 0.0; }
+    __syncthreads();
     if (input_had) fwht();
     for (int ss = s0 + dp.d[k] - 1; ss >= s; --ss) {   // un-apply the block's sublayers last .. s
         for (int i = n - 1; i >= 0; --i) {   // Ring^+ : the CNOTs in reverse order
             const int c = (i + 1) % n;
-            for (int z = 0; z < N; ++z) {
-                if (((z >> c) & 1) && !((z >> i) & 1)) {
-                    const int z1 = z | (1 << i);
-                    double t = vr[z][j]; vr[z][j] = vr[z1][j]; vr[z1][j] = t;
-                    t = vi[z][j]; vi[z][j] = vi[z1][j]; vi[z1][j] = t;
-                }
+            const int z = ((pi >> i) << (i + 1)) | (pi & ((1 << i) - 1)), z1 = z | (1 << i);
+            if ((z >> c) & 1) {
+                double t = vr[z][j]; vr[z][j] = vr[z1][j]; vr[z1][j] = t;
+                t = vi[z][j]; vi[z][j] = vi[z1][j]; vi[z1][j] = t;
             }
+            __syncthreads();
         }
-        __syncwarp();
-        if (j < n) {      // lane q computes U[ss, q] once
+        if (pi == 0 && j < n) {      // lane q computes U[ss, q] once
             const double a = (double)w[((int64_t)ss * 3 + 0) * n + j];
             const double b = (double)w[((int64_t)ss * 3 + 1) * n + j];
             const double c = (double)w[((int64_t)ss * 3 + 2) * n + j];
@@ -109,19 +107,17 @@ __device__ __forceinline__ void tc_prep_rev_body(const float* __restrict__ w, in
             uu[j][0] = cb * (cc * ca - sc * sa); uu[j][1] = -sb * (cc * ca + sc * sa);
             uu[j][2] = cb * (sc * ca + cc * sa); uu[j][3] = sb * (cc * sa - sc * ca);
         }
-        __syncwarp();
+        __syncthreads();
         for (int q = 0; q < n; ++q) {
             const double ar = uu[q][0], ai = uu[q][1], br = uu[q][2], bi = uu[q][3];
             // U^+ = [[conj(al), conj(be)], [-be, al]]
-            for (int z = 0; z < N; ++z) {
-                if (z & (1 << q)) continue;
-                const int z1 = z | (1 << q);
-                const double x0r = vr[z][j], x0i = vi[z][j], x1r = vr[z1][j], x1i = vi[z1][j];
-                vr[z][j] = ar * x0r + ai * x0i + br * x1r + bi * x1i;
-                vi[z][j] = ar * x0i - ai * x0r + br * x1i - bi * x1r;
-                vr[z1][j] = -br * x0r + bi * x0i + ar * x1r - ai * x1i;
-                vi[z1][j] = -br * x0i - bi * x0r + ar * x1i + ai * x1r;
-            }
+            const int z = ((pi >> q) << (q + 1)) | (pi & ((1 << q) - 1)), z1 = z | (1 << q);
+            const double x0r = vr[z][j], x0i = vi[z][j], x1r = vr[z1][j], x1i = vi[z1][j];
+            vr[z][j] = ar * x0r + ai * x0i + br * x1r + bi * x1i;
+            vi[z][j] = ar * x0i - ai * x0r + br * x1i - bi * x1r;
+            vr[z1][j] = -br * x0r + bi * x0i + ar * x1r - ai * x1i;
+            vi[z1][j] = -br * x0i - bi * x0r + ar * x1i + ai * x1r;
+            __syncthreads();
         }
     }
     fwht();     // EVERY cut of the reverse sweep is held in the Hadamard basis: one moment routine in the hot loop
@@ -135,7 +131,7 @@ __device__ __forceinline__ void tc_prep_rev_body(const float* __restrict__ w, in
         hi[o] = hh;
         lo[o] = ll;
     };
-    for (int i = 0; i < N; ++i) {
+    for (int i = pi; i < N; i += 16) {
         const double re = vr[i][j], im = vi[i][j];
         put(2 * i, 2 * j, re);
         put(2 * i, 2 * j + 1, -im);
@@ -144,7 +140,7 @@ __device__ __forceinline__ void tc_prep_rev_body(const float* __restrict__ w, in
     }
 }
 // forward images (CTAs 0 .. K-1) and reverse images (the rest) in ONE launch: the two sets are independent
-__global__ void __launch_bounds__(32) tc_prep_all_kernel(const float* __restrict__ w, int K, int S, DepthPack dp,
+__global__ void __launch_bounds__(512) tc_prep_all_kernel(const float* __restrict__ w, int K, int S, DepthPack dp,
                                                          unsigned char* __restrict__ bimg, unsigned char* __restrict__ rimg,
                                                          int per_block) {
     __shared__ double vr[32][33], vi[32][33], uu[5][4];
