@@ -144,7 +144,7 @@ hea_tc_rev_kernel(const HeaParams<float> p, const unsigned char* __restrict__ im
             constexpr uint32_t idesc_o = tc::idesc_f16(64, 64) | (1u << 15) | (1u << 16);      // A, B MN-major
             // operand rows: groups of 8 samples 1024 B apart (the K direction of the outer product), groups of 8
             // components 128 B apart (its M / N direction)
-            const uint32_t o_lbo = (flags & 2) ? 128u : 1024u, o_sbo = (flags & 2) ? 1024u : 128u;
+            constexpr uint32_t o_lbo = 1024u, o_sbo = 128u;      // (confirmed against the exact accumulator of a tile: tests/harness/tc_check_outer.py)
             const int64_t total = live_rounds(t) * p.K;
             auto fetch = [&](int64_t g) {
                 const int stage = (int)(g % NS);

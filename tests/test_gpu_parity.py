@@ -1142,3 +1142,24 @@ def test_tensor_tier_training_step_versions_agree(cuda_device):
     for v in (2, 3):
         for a, b in zip(res[1], res[v]):
             assert rel_l2(a, b) < TOL_F32, v
+
+
+def test_tensor_tier_huge_encoding_angles(cuda_device):
+    """Angles beyond the branch-free sin/cos range (|x| > 65,536: the out-of-line accurate path of the phase table) on
+    the tensor-core kernels, forward and both gradient kinds, against the fp64 oracle evaluated at the same fp32 inputs."""
+    from oracle import hea_oracle as orc
+    from quanonet_b200 import _lib
+    lib = _lib.load()
+    n, depths, B = 5, [2, 1, 2], 384
+    K, S = len(depths), sum(depths)
+    rng = np.random.default_rng(12)
+    x = rng.uniform(-np.pi, np.pi, (B, n * K)).astype(np.float32)
+    big = rng.random((B, n * K)) < 0.15
+    x[big] = (rng.uniform(7e4, 3e7, big.sum()) * rng.choice([-1.0, 1.0], big.sum())).astype(np.float32)
+    w = rng.uniform(-np.pi, np.pi, (S, 3, n)); g = rng.standard_normal(B)
+    try:
+        o, gx, gw = _tc_backward(lib, 1, g, x, w, depths, cuda_device, need_gx=True)
+    finally:
+        lib.qon_tensor_tier(1, 5121, None, None)
+    e_ref, gx_ref, gw_ref = orc.hea_forward_backward(x.astype(np.float64), w, n, [(n, d) for d in depths], orc.ham_from_bound(n), g)
+    assert rel_l2(o, e_ref) < TOL_F32 and rel_l2(gx, gx_ref) < TOL_F32 and rel_l2(gw, gw_ref) < TOL_F32
