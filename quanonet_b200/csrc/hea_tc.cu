@@ -9,6 +9,8 @@ namespace qon {
 // One CTA per SM as soon as there are that many tiles: a tile slot without a tile costs nothing (it stops after its last
 // live tile), and a lone tile has the SM to itself — so a mid-size batch spreads over all SMs instead of filling a few.
 static int tc_grid(int64_t B, int sms) {
+    static const int cap = [] { const char* e = getenv("QON_TC_GRID"); return e ? atoi(e) : 0; }();     // experiments only
+    if (cap > 0 && cap < sms) sms = cap;
     int64_t grid = (B + 127) / 128;
     if (grid > sms) grid = sms;
     return (int)(grid < 1 ? 1 : grid);
