@@ -25,6 +25,17 @@
 // columns: D psi | D lam | A psi (hi, lo) | A lam (hi, lo); the outer product's accumulator (M = 64: lanes 0..15 of each
 // subpartition) ALIASES the A psi columns — the MMA warp waits for the psi un-apply GEMM (bar_x) before issuing it, the
 // compute warps drain it (bar_g) before they write the next block's operand.
+//
+// One block of the sweep, per tile (every hand-off an mbarrier; every wait bounded, a time-out poisons the outputs):
+//   compute warps                                              MMA warp (one elected thread, uniform registers)
+//   split psi -> TMEM A psi + smem            -- bar_a  -->    psi un-apply GEMM (12 MMAs)              -- commit bar_x
+//   split lam -> TMEM A lam + smem (planar)   -- bar_a2 -->    lam un-apply GEMM (12 MMAs)              -- commit bar_d
+//   load this slot's running sums (global)                     wait bar_x; outer product (24 MMAs)      -- commit bar_g
+//   wait bar_x: tcgen05.ld psi, norm, sin/cos + phase table,   fetch the next block's image (cp.async.bulk)
+//               conjugate phases on psi        (under the lam GEMM)
+//   wait bar_d: tcgen05.ld lam, conjugate phases, encoding-angle gradients (tree), frequency-layer partial sums
+//   wait bar_g: tcgen05.ld.16x256b the outer product, fold re/im, add the running sums, store
+//   inputs of block k-1 (gathered a block ahead) -> angles
 #pragma once
 #include "hea_tc2.cuh"
 
