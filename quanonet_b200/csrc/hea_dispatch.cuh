@@ -70,6 +70,7 @@ cudaError_t hbm_run(const HeaParams<float>& p, const int* depth_host, int n, int
 
 // fp32 tensor-core tier (hea_tc.cu): n = 5, diagonal observables, every mode of hea_reg_inst.cuh
 size_t tc_workspace_bytes(int K, int S, int64_t B, int sms);
+bool tc_outer_supported(int K);
 cudaError_t tc_launch(int mode, int version, int sms, const HeaParams<float>& p, const float* w, const DepthPack& dp,
                       char* tc_ws, float* dbg, int* err_user, cudaStream_t st);
 

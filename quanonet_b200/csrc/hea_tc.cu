@@ -16,12 +16,16 @@ static int tc_grid(int64_t B, int sms) {
     return (int)(grid < 1 ? 1 : grid);
 }
 
+// The GEMM-form gradients keep 2 x grid accumulators of K x 8 KB: beyond this many blocks (2.4 GB at K = 1,024) the
+// per-sublayer-moment step is used instead.
+bool tc_outer_supported(int K) { return K <= kTcOuterMaxBlocks; }
+
 size_t tc_workspace_bytes(int K, int S, int64_t B, int sms) {
     // operand images + flags (error word, max |g| bits) + (training step) one 256-byte state row per sample + the
     // outer-product accumulators of the GEMM-form weight gradients: one per (CTA, tile slot) and block, + their fp64 sums
     return (size_t)(K + S) * kTcImgBytes + 256 +
-           (B > 0 ? (size_t)B * 256 + (size_t)2 * tc_grid(B, sms) * K * kTcAccLen * sizeof(float) +
-                        (size_t)K * kTcAccLen * sizeof(double) : 0);
+           (B > 0 ? (size_t)B * 256 + (tc_outer_supported(K) ? (size_t)2 * tc_grid(B, sms) * K * kTcAccLen * sizeof(float) +
+                                                                    (size_t)K * kTcAccLen * sizeof(double) : 0) : 0);
 }
 
 static int tc_flags() {
@@ -66,7 +70,8 @@ cudaError_t tc_launch(int mode, int version, int sms, const HeaParams<float>& p,
     unsigned* gmax = reinterpret_cast<unsigned*>(flag_block + 64);
     float* state = reinterpret_cast<float*>(flag_block + 256);
     float* gacc = reinterpret_cast<float*>(flag_block + 256 + (size_t)(p.B > 0 ? p.B : 0) * 256);
-    const bool outer = grad && version == 4;
+    const bool outer = grad && version == 4 && tc_outer_supported(p.K);
+    if (grad && version == 4 && !outer) version = 2;
     cudaError_t e = cudaMemsetAsync(flag_block, 0, 256, st);      // (a caller-provided error word is the caller's to clear)
     if (e != cudaSuccess) return e;
     if (grad) tc_prep_all_kernel<<<p.K + (outer ? p.K : p.S), 512, 0, st>>>(w, p.K, p.S, dp, img, img + (size_t)p.K * kTcImgBytes, outer ? 1 : 0);

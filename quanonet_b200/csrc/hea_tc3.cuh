@@ -50,6 +50,7 @@ struct TcRev {
     static constexpr int SMEM = NT * TILE_SMEM;
     static constexpr int REGS_COMPUTE = 232, REGS_MMA = 40;
 };
+constexpr int kTcOuterMaxBlocks = 256;
 constexpr int kTcAccLen = 2048;                              // floats per (slot, block): the 32 x 32 complex Y in fragment order
 
 // power of two above max |g| (bits from the forward kernel); NaN / inf poison the step

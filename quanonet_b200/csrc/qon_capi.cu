@@ -665,7 +665,7 @@ int run(const Job& j) {
             if constexpr (sizeof(T) == 4) {
                 int dev; DeviceInfo di;
                 if (!device_info(&dev, &di)) return fail(QON_ERR_NO_DEVICE, "no usable CUDA device");
-                const int version = tcc.enable == 3 ? 3 : tcc.enable == 2 ? 2 : 4;
+                const int version = tcc.enable == 3 ? 3 : (tcc.enable == 2 || !tc_outer_supported(K)) ? 2 : 4;
                 e = tc_launch(mode, version, di.sms, (const HeaParams<float>&)p, (const float*)j.w, dp,
                               base + pl.off_tc, tcc.dbg, tcc.err, st);
                 if (j.grad) {

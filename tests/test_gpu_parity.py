@@ -1163,3 +1163,19 @@ def test_tensor_tier_huge_encoding_angles(cuda_device):
         lib.qon_tensor_tier(1, 5121, None, None)
     e_ref, gx_ref, gw_ref = orc.hea_forward_backward(x.astype(np.float64), w, n, [(n, d) for d in depths], orc.ham_from_bound(n), g)
     assert rel_l2(o, e_ref) < TOL_F32 and rel_l2(gx, gx_ref) < TOL_F32 and rel_l2(gw, gw_ref) < TOL_F32
+
+
+def test_tensor_tier_many_blocks_falls_back_to_string_moments(cuda_device):
+    """More than 256 encoding blocks: the GEMM-form gradients would need 2 x grid x K x 8 KB of accumulators, so the
+    tier switches to its per-sublayer-moment step on its own; results stay at parity with the register kernels."""
+    from quanonet_b200 import _lib
+    lib = _lib.load()
+    n, depths, B = 5, [1] * 300, 700
+    rng = np.random.default_rng(14)
+    x = rng.uniform(-np.pi, np.pi, (B, n * 300)); w = rng.uniform(-np.pi, np.pi, (300, 3, n)); g = rng.standard_normal(B)
+    try:
+        o1, gx1, gw1 = _tc_backward(lib, 1, g, x, w, depths, cuda_device, need_gx=True)
+        o0, gx0, gw0 = _tc_backward(lib, 0, g, x, w, depths, cuda_device, need_gx=True)
+    finally:
+        lib.qon_tensor_tier(1, 5121, None, None)
+    assert rel_l2(o1, o0) < 3 * TOL_F32 and rel_l2(gx1, gx0) < 3 * TOL_F32 and rel_l2(gw1, gw0) < 3 * TOL_F32
