@@ -28,6 +28,9 @@ namespace qon {
 #ifndef QON_TC_SLOW_INLINE
 #define QON_TC_SLOW_INLINE 0      // experiment switch (scripts/build_tc_variant.sh): huge-angle sin/cos inlined instead of called
 #endif
+#ifndef QON_TC_REV_REGS
+#define QON_TC_REV_REGS 232       // experiment switch: registers of the reverse kernel's compute warps (the MMA warpgroup keeps the rest)
+#endif
 #ifndef QON_TC_REV_STAGES
 #define QON_TC_REV_STAGES 2       // experiment switch (scripts/build_tc_variant.sh): B-image ring stages per tile in the reverse kernel
 #endif

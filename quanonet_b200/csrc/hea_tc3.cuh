@@ -48,7 +48,7 @@ struct TcRev {
     static constexpr int OPER_BYTES = 65536;                 // per tile: psi hi | psi lo | lam hi | lam lo, 16 KB each
     static constexpr int TILE_SMEM = OPER_BYTES + NS * kTcImgBytes;
     static constexpr int SMEM = NT * TILE_SMEM;
-    static constexpr int REGS_COMPUTE = 232, REGS_MMA = 40;
+    static constexpr int REGS_COMPUTE = QON_TC_REV_REGS, REGS_MMA = (168 * 384 - 256 * QON_TC_REV_REGS) / 128;      // 232 / 40
 };
 constexpr int kTcOuterMaxBlocks = 256;
 constexpr int kTcAccLen = 2048;                              // floats per (slot, block): the 32 x 32 complex Y in fragment order
@@ -166,7 +166,8 @@ hea_tc_rev_kernel(const HeaParams<float> p, const unsigned char* __restrict__ im
             };
             for (int64_t g = 0; g < (NS > 1 ? NS - 1 : 1) && g < total; ++g) fetch(g);
             bool dead = false;
-            uint32_t apar = 0, xpar = 0, dpar_m = 0;
+            uint32_t apar = 0, xpar = 0;
+            [[maybe_unused]] uint32_t dpar_m = 0;
             auto gemm = [&](uint32_t d, uint32_t a, uint32_t sb) {      // D = A_hi B_hi + A_hi B_lo + A_lo B_hi
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
