@@ -464,11 +464,11 @@ def run_b200(args):
                     "timer": "max(CUDA events, host wall clock) over the K steps, max over ranks"},
             # this library's kernels per step: prep, circuit kernel, finalize (+ finalize_enc) — with N > 1 the
             # finalize kernel is also the all-reduce (finalize_exchange_kernel), else one peer all-reduce kernel more;
-            # the tensor-core tier adds its two operand-image prep kernels, runs the step as forward-only + reverse-only
-            # kernels and turns the batch-summed outer products into Pauli moments in two more (tc_slot_reduce_kernel,
-            # tc_moment_kernel)
+            # the tensor-core tier adds its operand-image prep kernel (tc_prep_all_kernel), runs the step as forward-only +
+            # reverse kernels and turns the batch-summed outer products into Pauli moments in two more
+            # (tc_slot_reduce_kernel, tc_moment_kernel): prep, tc_prep_all, forward, reverse, slot sums, moments, finalize x2
             "gpu_launches": ((3 if getattr(trainer, "_fused_exchange", False) else
-                              (4 if trainer.fused_encoding else 3) + (1 if world > 1 else 0)) + (5 if tc_on else 0)) * K,
+                              (4 if trainer.fused_encoding else 3) + (1 if world > 1 else 0)) + (4 if tc_on else 0)) * K,
             "roofline": {"bound": "fp32", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                          "frac": achieved / peak if peak else None, "traffic": traffic,
                          "kernel": ("hea_tc_kernel<forward> + hea_tc_rev_kernel<grad%s> (tcgen05: block-unitary GEMMs, batch-summed outer products for the weight gradients; FFMA2 phases; +prep, tc_moment_kernel, finalize)"
