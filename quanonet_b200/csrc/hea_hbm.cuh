@@ -92,8 +92,11 @@ __host__ __device__ __forceinline__ unsigned hbm_gidx(unsigned l, unsigned t, in
 #ifndef QON_HBM_FWD_BLOCKS
 #define QON_HBM_FWD_BLOCKS 5      // resident CTAs per SM the forward pass kernels (TB = 12) are compiled for: 5 x 128 threads at 96 registers measured +3 % over 4 at 123 (6 at 80: -9 %)
 #endif
+#ifndef QON_HBM_REV_BLOCKS
+#define QON_HBM_REV_BLOCKS 3      // the same for the reverse pass kernels (psi + lam tiles: 64 KB per CTA): 3 CTAs at 168 registers measured -7 % time at n = 16 against 2 at 247
+#endif
 template <bool REVERSE, int TB, bool BULK>
-__global__ void __launch_bounds__(1 << (TB - 5), REVERSE ? (TB == 13 ? 1 : 2) : (TB == 13 ? 2 : QON_HBM_FWD_BLOCKS))
+__global__ void __launch_bounds__(1 << (TB - 5), REVERSE ? (TB == 13 ? 1 : QON_HBM_REV_BLOCKS) : (TB == 13 ? 2 : QON_HBM_FWD_BLOCKS))
 hea_hbm_pass_kernel(const HeaParams<float> p, const HbmPass hp, const HbmBuffers hb) {
     using State = SmemState;
     constexpr int THREADS = 1 << (TB - 5);
